@@ -1,0 +1,44 @@
+"""ctypes binding of libb200lmd.so (the C ABI declared in include/b200lmd.h).
+
+There is no CPU fallback: if the shared library is missing, importing a symbol raises immediately.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200lmd.so")
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(
+                f"{LIB_PATH} not built - run `python -c 'import __graft_entry__ as g; g.build()'` (there is no "
+                "CPU or PyTorch fallback for the B200 path)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.b200lmd_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error(lib().b200lmd_last_error().decode())
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
