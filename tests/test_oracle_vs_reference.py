@@ -1,0 +1,192 @@
+"""Pins the oracle restatement (oracle/*.py) against the UNMODIFIED reference imported from /root/reference.
+
+CPU only; runs in the build container (skipped where /root/reference is absent, e.g. on the GPU box).  The reference
+has no tests or golden vectors of its own, so outputs of the reference itself, run here on seeded
+synthetic weights, are the pin; oracle/make_goldens.py freezes the same cases into tests/golden/.
+"""
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import guidance_ref, pipeline_ref, ref_loader, unet_ref
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+
+
+def test_scale_proportion_matches_reference():
+    r = ref_loader.load()
+    rng = random.Random(0)
+    for _ in range(3000):
+        x0, y0 = rng.uniform(-0.1, 0.9), rng.uniform(-0.1, 0.9)
+        box = (x0, y0, x0 + rng.uniform(0, 0.8), y0 + rng.uniform(0, 0.8))
+        for side in (8, 16, 24, 64):
+            assert guidance_ref.scale_proportion(box, side, side) == r.utils.scale_proportion(box, side, side)
+    # .5 cases (banker's rounding)
+    for box in [(0.0625, 0.1875, 0.5625, 0.8125), (0.03125, 0.09375, 0.15625, 0.21875)]:
+        for side in (8, 16):
+            assert guidance_ref.scale_proportion(box, side, side) == r.utils.scale_proportion(box, side, side)
+
+
+def _random_case(seed, heads=8, with_ref=True):
+    g = torch.Generator().manual_seed(seed)
+    rng = random.Random(seed)
+    saved = {}
+    for k in KEYS:
+        n = 64 if k[0] == "mid" else 256
+        saved[k] = torch.softmax(3 * torch.randn(1, heads, n, 77, generator=g), dim=-1)
+    n_obj = rng.randint(1, 3)
+    bboxes, positions, words, refs = [], [], [], []
+    tok = 1
+    for o in range(n_obj):
+        nb = rng.randint(1, 2)
+        boxes = []
+        for _ in range(nb):
+            w_, h_ = rng.uniform(0.15, 0.6), rng.uniform(0.15, 0.6)
+            x, y = rng.uniform(0, 1 - w_), rng.uniform(0, 1 - h_)
+            boxes.append((x, y, x + w_, y + h_))
+        bboxes.append(boxes)
+        nt = rng.randint(1, 3)
+        positions.append(list(range(tok, tok + nt)))
+        words.append(tok + nt - 1)
+        tok += nt + 1
+        refs.append([[{k: torch.softmax(3 * torch.randn(1, heads, saved[k].shape[2], 1, generator=g), dim=2)
+                       for k in KEYS}] for _ in range(nb)])   # [box][step=0][key]
+    return saved, bboxes, positions, words, (refs if with_ref else None)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("with_ref", [False, True])
+def test_ca_loss_and_grad_match_reference(seed, with_ref):
+    r = ref_loader.load()
+    saved, bboxes, positions, words, refs = _random_case(seed, with_ref=with_ref)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in saved.items()}
+    kw = dict(fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=4.0, use_ratio_based_loss=False)
+    L_ref = r.guidance.compute_ca_lossv3(leaf, bboxes, positions, KEYS, ref_ca_saved_attns=refs, index=0,
+                                         ref_ca_word_token_only=True, word_token_indices=words,
+                                         ref_ca_loss_weight=2.0, **kw)
+    g_ref = torch.autograd.grad(L_ref, [leaf[k] for k in KEYS])
+    one = {k: v[0] for k, v in saved.items()}
+    ref_maps = None
+    if refs is not None:
+        ref_maps = [[{k: box[0][k][0, :, :, 0] for k in KEYS} for box in obj] for obj in refs]
+    L = guidance_ref.ca_loss(one, bboxes, positions, KEYS, 0.2, 0.2, 1.0, 4.0, ref_maps, words, 2.0, True)
+    assert abs(float(L) - float(L_ref)) < 2e-6 * max(1.0, abs(float(L_ref)))
+    L2, grads = guidance_ref.ca_loss_and_grad({k: v.numpy() for k, v in one.items()}, bboxes, positions, KEYS, 0.2,
+                                              0.2, 1.0, 4.0,
+                                              None if ref_maps is None else
+                                              [[{k: m[k].numpy() for k in KEYS} for m in obj] for obj in ref_maps],
+                                              words, 2.0, True)
+    assert abs(L2 - float(L_ref)) < 5e-6 * max(1.0, abs(float(L_ref)))
+    for k, gr in zip(KEYS, g_ref):
+        np.testing.assert_allclose(grads[k], gr[0].numpy(), rtol=2e-4, atol=2e-7)
+
+
+@pytest.mark.parametrize("gligen", [False, True])
+def test_unet_forward_matches_reference(gligen):
+    from oracle import refrun
+    cfg = unet_ref.UNetConfig.tiny(gligen=gligen)
+    w = unet_ref.make_weights(cfg, seed=0)
+    m = refrun.build_reference_unet(cfg, w)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    kw = {"save_attn_to_dict": {}, "save_keys": None, "enable_flash_attn": False}
+    gl = None
+    if gligen:
+        gl = dict(boxes=torch.rand(2, 30, 4, generator=g), masks=(torch.rand(2, 30, generator=g) > 0.8).float(),
+                  positive_embeddings=torch.randn(2, 30, 768, generator=g))
+        kw["gligen"] = dict(gl)
+    with torch.no_grad():
+        ref = m(x, 481, encoder_hidden_states=ctx, cross_attention_kwargs=kw).sample
+        saved = {}
+        mine = unet_ref.unet_forward(w, cfg, x, 481, ctx, gligen=gl, saved=saved)
+    assert (ref - mine).abs().max() < 2e-5
+    assert len(saved) == 16
+    for k, v in kw["save_attn_to_dict"].items():
+        assert (v - saved[k]).abs().max() < 1e-4
+
+
+def _setup_pipeline(gligen):
+    from oracle import refrun
+    cfg = unet_ref.UNetConfig.tiny(gligen=gligen)
+    w = unet_ref.make_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(5)
+    z0 = torch.randn(1, 4, 32, 32, generator=g)
+    uncond = torch.randn(1, 77, 768, generator=g)
+    cond = torch.randn(1, 77, 768, generator=g)
+    table = torch.randn(4, 768, generator=g)
+    tok = refrun.FakeTokenizer({"a cat": 0, "a dog": 1})
+    enc = refrun.FakeTextEncoder(table)
+    r, md = refrun.model_dict(cfg, w, tok, enc)
+    return cfg, w, r, md, z0, uncond, cond, table
+
+
+def test_semantic_guidance_loop_matches_reference():
+    """generate_semantic_guidance (LMD per-box phase, backward_guidance): guidance + CFG + DDIM, attention saving"""
+    cfg, w, r, md, z0, uncond, cond, _ = _setup_pipeline(False)
+    bboxes = [[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9)]]
+    positions = [[2, 3], [6]]
+    steps = 4
+    kw = dict(loss_scale=30, loss_threshold=0.2, max_iter=[2, 1, 1], max_index_step=3, guidance_attn_keys=KEYS,
+              fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=4.0, use_ratio_based_loss=False,
+              ref_ca_loss_weight=0.5, verbose=False)
+    out = r.pipelines.generate_semantic_guidance(
+        md, z0, (torch.cat([uncond, cond]), uncond, cond), steps, bboxes, ["a cat", "a dog"], positions,
+        semantic_guidance_kwargs=kw, return_saved_cross_attn=True, saved_cross_attn_keys=[("down", 2, 1, 0)] + KEYS,
+        return_cond_ca_only=True, return_token_ca_only=3, save_all_latents=True, show_progress=False)
+    lat_ref, _, saved_ref, all_ref = out
+    g = pipeline_ref.GuidanceCfg(bboxes, positions, KEYS, 30, 0.2, [2, 1, 1], 3, 0.2, 0.2, 1.0, 4.0)
+    res = pipeline_ref.denoise(w, cfg, z0, uncond, cond, steps, g=g, save_keys=[("down", 2, 1, 0)] + KEYS,
+                               save_token=3)
+    assert res["iters"] == [2, 1, 1, 0]
+    assert (res["latents"] - lat_ref).abs().max() < 5e-3
+    assert (res["latents_all"] - all_ref).abs().max() < 5e-3
+    for s_ref, s in zip(saved_ref, res["saved"]):
+        for k in s_ref:
+            assert s_ref[k].shape == s[k].shape
+            assert (s_ref[k] - s[k]).abs().max() < 1e-3
+
+
+def test_gligen_loop_with_ref_attention_matches_reference():
+    """generate_gligen (LMD+ overall phase): fuser schedule, null-mask guidance pass, ref-attention loss, frozen blend"""
+    cfg, w, r, md, z0, uncond, cond, table = _setup_pipeline(True)
+    steps = 4
+    g0 = torch.Generator().manual_seed(9)
+    frozen_latents = torch.randn(steps + 1, 1, 4, 32, 32, generator=g0)
+    frozen_latents[0] = z0
+    frozen_mask = (torch.rand(32, 32, generator=g0) > 0.5).float()
+    bboxes_flat = [(0.1, 0.2, 0.6, 0.7), (0.5, 0.4, 0.95, 0.9)]
+    phrases = ["a cat", "a dog"]
+    sg_bboxes = [[bboxes_flat[0]], [bboxes_flat[1]]]
+    positions = [[2, 3], [6]]
+    words = [3, 6]
+    heads = 8
+    refs = [[[{k: torch.softmax(3 * torch.randn(1, heads, 16 if k[0] == "mid" else 64, 1, generator=g0), dim=2)
+               for k in KEYS} for _ in range(steps)]] for _ in range(2)]   # [obj][box][step][key]
+    kw = dict(loss_scale=5, loss_threshold=0.01, max_iter=[2, 1], max_index_step=3, guidance_attn_keys=KEYS,
+              fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=4.0, use_ratio_based_loss=False,
+              ref_ca_saved_attns=refs, ref_ca_word_token_only=True, word_token_indices=words, ref_ca_loss_weight=2.0,
+              verbose=False)
+    lat_ref, _ = r.pipelines.generate_gligen(
+        md, frozen_latents, (uncond, cond), steps, bboxes_flat, phrases, gligen_scheduled_sampling_beta=0.5,
+        frozen_steps=2, frozen_mask=frozen_mask, semantic_guidance=True, semantic_guidance_bboxes=sg_bboxes,
+        semantic_guidance_object_positions=positions, semantic_guidance_kwargs=kw, show_progress=False)
+    boxes = torch.zeros(1, 30, 4)
+    boxes[0, :2] = torch.tensor(bboxes_flat)
+    emb = torch.zeros(1, 30, 768)
+    emb[0, :2] = table[:2]
+    masks = torch.zeros(1, 30)
+    masks[0, :2] = 1
+    ref_maps = [[[{k: st[k][0, :, :, 0] for k in KEYS} for st in box] for box in obj] for obj in refs]
+    g = pipeline_ref.GuidanceCfg(sg_bboxes, positions, KEYS, 5, 0.01, [2, 1], 3, 0.2, 0.2, 1.0, 4.0, ref_maps, words,
+                                 2.0, True)
+    res = pipeline_ref.denoise(w, cfg, z0, uncond, cond, steps, g=g, frozen_mask=frozen_mask,
+                               frozen_latents=frozen_latents, frozen_steps=2,
+                               gligen=dict(boxes=boxes, masks=masks, positive_embeddings=emb), gligen_beta=0.5)
+    assert res["iters"] == [2, 1, 1, 0]
+    assert (res["latents"] - lat_ref).abs().max() < 5e-3
