@@ -41,6 +41,42 @@ int b200lmd_linear_geglu_f16(const void* x, int ldx, const void* w_il, const voi
 int b200lmd_conv3x3_f16(const void* x, const void* w, const void* bias, const void* chan_add, const void* residual,
                         void* y, void* y_f32, int B, int H, int W, int Cin, int Cout, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ attention
+ * Head-split projection: [M, nproj*C] = x[M,K] . W[nproj*C, K]^T scattered into per-head operand slabs
+ * (to_q / to_k / to_v of models/attention_processor.py:426-438 plus head_to_batch_dim :190-199 in one pass):
+ *   q  [B*heads, q_alloc, dp]  (projection index 0)      dp  = head_dim rounded up to 64, zero padded
+ *   k  [B*heads, k_alloc, dp]  (projection index 1)
+ *   vt [B*heads, d16, v_alloc] (projection index 2, stored d-major = V^T), d16 = b200lmd_round_d16(head_dim)
+ * `which0` is the projection index of column 0 of W (so K/V-only or Q-only projections reuse the call).
+ * Slabs must be zero-initialised once (padding is never written). rows_per_img = tokens per image in x. */
+int b200lmd_round_dp(int head_dim);
+int b200lmd_round_d16(int head_dim);
+int b200lmd_project_heads_f16(const void* x, int ldx, const void* w, int M, int N, int K, int rows_per_img, int heads,
+                              int head_dim, int which0, void* q, int q_alloc, void* k, int k_alloc, void* vt,
+                              int v_alloc, void* stream);
+
+/* softmax(scale * q k^T) v over the slabs above -> out[B*nq, ldo] (head h at columns h*d..), lse2 (optional, fp32
+ * [B*heads, q_alloc], log2-domain row statistic kept for the backward).  Replaces F.scaled_dot_product_attention at
+ * models/attention_processor.py:355 and the baddbmm/softmax/bmm path :216-233,447 when no map is requested. */
+int b200lmd_attention_fwd_f16(const void* q, const void* k, const void* vt, void* out, int ldo, void* lse2, int B,
+                              int heads, int nq, int nk, int q_alloc, int k_alloc, int head_dim, float scale,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------ normalisation
+ * GroupNorm (+ optional SiLU) over NHWC fp16 x[B, n, C]: stats then apply (torch.nn.GroupNorm inside diffusers
+ * ResnetBlock2D and models/transformer_2d.py:146,283).  sums: fp32 [B, groups, 2] scratch (zeroed by the call). */
+int b200lmd_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* sums, int B, int n, int C,
+                          int groups, float eps, int silu, void* stream);
+int b200lmd_groupnorm_bwd_f16(const void* dy, const void* x, const void* sums, const void* gamma, const void* beta,
+                              void* dx, void* bsums, int B, int n, int C, int groups, float eps, int silu,
+                              int accumulate, void* stream);
+/* LayerNorm over the last dim of x[rows, C] (models/attention.py:114,133,149); stats fp32 [rows, 2] or NULL. */
+int b200lmd_layernorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* stats, long long rows,
+                          int C, float eps, void* stream);
+int b200lmd_layernorm_bwd_f16(const void* dy, const void* x, const void* stats, const void* gamma, void* dx,
+                              long long rows, int C, int accumulate, void* stream);
+int b200lmd_geglu_bwd_f16(const void* pre, const void* dy, void* dpre, long long rows, int F, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

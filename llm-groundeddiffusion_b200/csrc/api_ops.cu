@@ -2,6 +2,8 @@
 #include <string>
 
 #include "../../include/b200lmd.h"
+#include "attention_host.cuh"
+#include "elementwise.cuh"
 #include "gemm_host.cuh"
 
 namespace b200 {
@@ -117,5 +119,109 @@ extern "C" int b200lmd_conv3x3_f16(const void* x, const void* w, const void* bia
     ep.out_f32 = (float*)y_f32; ep.ldo32 = Cout;
     ep.OH = H; ep.OW = W;
     run_gemm(build_gemm(b, ep), (cudaStream_t)stream);
+  });
+}
+
+extern "C" int b200lmd_round_dp(int d) { return round_dp(d); }
+extern "C" int b200lmd_round_d16(int d) {
+  try { return round_d16(d); } catch (...) { return -1; }
+}
+
+extern "C" int b200lmd_project_heads_f16(const void* x, int ldx, const void* w, int M, int N, int K, int rows_per_img,
+                                         int heads, int head_dim, int which0, void* q, int q_alloc, void* k,
+                                         int k_alloc, void* vt, int v_alloc, void* stream) {
+  return guarded([&] {
+    if (head_dim % 8) throw std::runtime_error("head_dim must be a multiple of 8");
+    GemmBuild b;
+    b.A = (const __half*)x; b.aW = M; b.a_ld = ldx; b.Cin = K;
+    b.Wt = (const __half*)w; b.N = N;
+    b.gW = M;
+    b.taps[0] = GemmTap{0, 0, 0, 0};
+    GemmParams ep = default_epilogue();
+    ep.mode = EPI_HEADS;
+    ep.rows_per_img = rows_per_img;
+    ep.C = heads * head_dim; ep.heads = heads; ep.d = head_dim; ep.which0 = which0;
+    ep.dp = round_dp(head_dim); ep.d16 = round_d16(head_dim);
+    ep.rm[0] = (__half*)q; ep.rm_alloc[0] = q_alloc;
+    ep.rm[1] = (__half*)k; ep.rm_alloc[1] = k_alloc;
+    ep.tr[2] = (__half*)vt; ep.tr_alloc[2] = v_alloc;
+    ep.OH = 1; ep.OW = M;
+    run_gemm(build_gemm(b, ep), (cudaStream_t)stream);
+  });
+}
+
+extern "C" int b200lmd_attention_fwd_f16(const void* q, const void* k, const void* vt, void* out, int ldo, void* lse2,
+                                         int B, int heads, int nq, int nk, int q_alloc, int k_alloc, int head_dim,
+                                         float scale, void* stream) {
+  return guarded([&] {
+    run_attn_fwd(build_attn_fwd((const __half*)q, (const __half*)k, (const __half*)vt, (__half*)out, ldo,
+                                (float*)lse2, B, heads, nq, nk, q_alloc, k_alloc, head_dim, scale),
+                 (cudaStream_t)stream);
+  });
+}
+
+static int gn_rows_per(int B, int n) {
+  // aim for ~2 waves of blocks over (chunks x B)
+  int chunks = (2 * kNumSMs + B - 1) / B;
+  int rp = (n + chunks - 1) / chunks;
+  return rp < 4 ? 4 : rp;
+}
+
+extern "C" int b200lmd_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* sums, int B,
+                                     int n, int C, int groups, float eps, int silu, void* stream) {
+  return guarded([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 8 || C % groups) throw std::runtime_error("GroupNorm: C must be a multiple of 8 and of groups");
+    B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * B * groups, st));
+    const int rp = gn_rows_per(B, n);
+    dim3 grid((n + rp - 1) / rp, B);
+    gn_stats_kernel<<<grid, 256, groups * 2 * sizeof(float), st>>>((const __half*)x, (float*)sums, n, C, groups, rp);
+    gn_apply_kernel<<<ew_grid((long long)B * n * (C / 8)), 256, 0, st>>>((const __half*)x, (const float*)sums,
+                                                                        (const float*)gamma, (const float*)beta,
+                                                                        (__half*)y, B, n, C, groups, eps, silu);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+
+extern "C" int b200lmd_groupnorm_bwd_f16(const void* dy, const void* x, const void* sums, const void* gamma,
+                                         const void* beta, void* dx, void* bsums, int B, int n, int C, int groups,
+                                         float eps, int silu, int accumulate, void* stream) {
+  return guarded([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200_CHECK(cudaMemsetAsync(bsums, 0, sizeof(float) * 2 * B * groups, st));
+    const int rp = gn_rows_per(B, n);
+    dim3 grid((n + rp - 1) / rp, B);
+    gn_bwd_stats_kernel<<<grid, 256, groups * 2 * sizeof(float), st>>>((const __half*)dy, (const __half*)x,
+                                                                      (const float*)sums, (const float*)gamma,
+                                                                      (const float*)beta, (float*)bsums, n, C, groups,
+                                                                      eps, silu, rp);
+    gn_bwd_apply_kernel<<<ew_grid((long long)B * n * (C / 8)), 256, 0, st>>>(
+        (const __half*)dy, (const __half*)x, (const float*)sums, (const float*)bsums, (const float*)gamma,
+        (const float*)beta, (__half*)dx, B, n, C, groups, eps, silu, accumulate);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+
+extern "C" int b200lmd_layernorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* stats,
+                                     long long rows, int C, float eps, void* stream) {
+  return guarded([&] {
+    ln_fwd_kernel<<<ew_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, (const float*)gamma, (const float*)beta, (__half*)y, (float*)stats, rows, C, eps);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+extern "C" int b200lmd_layernorm_bwd_f16(const void* dy, const void* x, const void* stats, const void* gamma, void* dx,
+                                         long long rows, int C, int accumulate, void* stream) {
+  return guarded([&] {
+    ln_bwd_kernel<<<ew_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)dy, (const __half*)x, (const float*)stats, (const float*)gamma, (__half*)dx, rows, C, accumulate);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+extern "C" int b200lmd_geglu_bwd_f16(const void* pre, const void* dy, void* dpre, long long rows, int F, void* stream) {
+  return guarded([&] {
+    geglu_bwd_kernel<<<ew_grid(rows * (F / 8)), 256, 0, (cudaStream_t)stream>>>((const __half*)pre, (const __half*)dy,
+                                                                              (__half*)dpre, rows, F);
+    B200_CHECK(cudaGetLastError());
   });
 }

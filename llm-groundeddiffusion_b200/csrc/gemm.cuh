@@ -52,9 +52,9 @@ struct GemmParams {
   int C;                   // channels per projection (heads*d)
   int heads, d;
   int which0;              // projection index of column 0 (0 = Q, 1 = K, 2 = V)
-  __half* hq; int q_dp; int q_tok_alloc;     // [B, heads, q_tok_alloc, q_dp]
-  __half* hk; int k_dp; int k_tok_alloc;     // [B, heads, k_tok_alloc, k_dp]
-  __half* hvt; int v_d16; int v_tok_alloc;   // [B, heads, v_d16, v_tok_alloc]
+  int dp, d16;             // padded head dims of the row-major / transposed slabs
+  __half* rm[3]; int rm_alloc[3];   // row-major slab per projection  [B*heads, rm_alloc, dp]   (or null)
+  __half* tr[3]; int tr_alloc[3];   // transposed slab per projection [B*heads, d16, tr_alloc]  (or null)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -253,20 +253,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int j0 = cc % p.d;
             const int tok = (int)(orow % p.rows_per_img);
             const long long bh = (long long)img * p.heads + head;
-            if (which == 2) {
-              __half* dst = p.hvt + (bh * p.v_d16 + j0) * (long long)p.v_tok_alloc + tok;
+            if (p.tr[which]) {
+              __half* dst = p.tr[which] + (bh * p.d16 + j0) * (long long)p.tr_alloc[which] + tok;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[(long long)j * p.v_tok_alloc] = __float2half_rn(f[j]);
-            } else {
-              __half* base = (which == 0) ? p.hq : p.hk;
-              const int dp = (which == 0) ? p.q_dp : p.k_dp;
-              const int ta = (which == 0) ? p.q_tok_alloc : p.k_tok_alloc;
+              for (int j = 0; j < 8; ++j) dst[(long long)j * p.tr_alloc[which]] = __float2half_rn(f[j]);
+            }
+            if (p.rm[which]) {
               uint4 st;
               st.x = pack_h2(f[0], f[1]);
               st.y = pack_h2(f[2], f[3]);
               st.z = pack_h2(f[4], f[5]);
               st.w = pack_h2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(base + (bh * ta + tok) * (long long)dp + j0) = st;
+              *reinterpret_cast<uint4*>(p.rm[which] + (bh * p.rm_alloc[which] + tok) * (long long)p.dp + j0) = st;
             }
           }
         }

@@ -51,3 +51,86 @@ def conv3x3(x, w, bias=None, chan_add=None, residual=None, out_f32=False):
     check(lib().b200lmd_conv3x3_f16(ptr(x), ptr(w), ptr(bias), ptr(chan_add), ptr(residual), ptr(y), ptr(y32), _i(B),
                                     _i(H), _i(W), _i(Cin), _i(Cout), cur_stream()))
     return (y, y32) if out_f32 else y
+
+
+def round_dp(d):
+    return lib().b200lmd_round_dp(_i(d))
+
+
+def round_d16(d):
+    return lib().b200lmd_round_d16(_i(d))
+
+
+def alloc_head_slabs(B, heads, d, n_alloc_q, n_alloc_k, device):
+    dp, d16 = round_dp(d), round_d16(d)
+    q = torch.zeros(B * heads, n_alloc_q, dp, device=device, dtype=torch.float16)
+    k = torch.zeros(B * heads, n_alloc_k, dp, device=device, dtype=torch.float16)
+    vt = torch.zeros(B * heads, d16, n_alloc_k, device=device, dtype=torch.float16)
+    return q, k, vt
+
+
+def project_heads(x, w, rows_per_img, heads, d, which0, q=None, k=None, vt=None):
+    """x [M,K] @ w[nproj*C, K]^T scattered into slabs (see include/b200lmd.h)"""
+    M, K = x.shape
+    N = w.shape[0]
+    check(lib().b200lmd_project_heads_f16(ptr(x), _i(x.stride(0)), ptr(w), _i(M), _i(N), _i(K), _i(rows_per_img),
+                                          _i(heads), _i(d), _i(which0), ptr(q), _i(q.shape[1] if q is not None else 0),
+                                          ptr(k), _i(k.shape[1] if k is not None else 0), ptr(vt),
+                                          _i(vt.shape[2] if vt is not None else 0), cur_stream()))
+
+
+def attention_fwd(q, k, vt, B, heads, nq, nk, d, scale, want_lse=False):
+    out = torch.empty(B * nq, heads * d, device=q.device, dtype=torch.float16)
+    lse = torch.zeros(B * heads, q.shape[1], device=q.device, dtype=torch.float32) if want_lse else None
+    check(lib().b200lmd_attention_fwd_f16(ptr(q), ptr(k), ptr(vt), ptr(out), _i(heads * d), ptr(lse), _i(B), _i(heads),
+                                          _i(nq), _i(nk), _i(q.shape[1]), _i(k.shape[1]), _i(d), _f(scale),
+                                          cur_stream()))
+    return (out, lse) if want_lse else out
+
+
+def groupnorm(x, gamma, beta, groups, eps, silu, want_sums=False):
+    """x [B, n, C] fp16"""
+    B, n, C = x.shape
+    y = torch.empty_like(x)
+    sums = torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
+    check(lib().b200lmd_groupnorm_f16(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(sums), _i(B), _i(n), _i(C),
+                                      _i(groups), _f(eps), _i(int(silu)), cur_stream()))
+    return (y, sums) if want_sums else y
+
+
+def groupnorm_bwd(dy, x, sums, gamma, beta, groups, eps, silu, dx=None):
+    B, n, C = x.shape
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty_like(x)
+    bsums = torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
+    check(lib().b200lmd_groupnorm_bwd_f16(ptr(dy), ptr(x), ptr(sums), ptr(gamma), ptr(beta), ptr(dx), ptr(bsums), _i(B),
+                                          _i(n), _i(C), _i(groups), _f(eps), _i(int(silu)), _i(int(acc)),
+                                          cur_stream()))
+    return dx
+
+
+def layernorm(x, gamma, beta, eps=1e-5, want_stats=False):
+    rows, C = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if want_stats else None
+    check(lib().b200lmd_layernorm_f16(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), ctypes.c_longlong(rows),
+                                      _i(C), _f(eps), cur_stream()))
+    return (y, stats) if want_stats else y
+
+
+def layernorm_bwd(dy, x, stats, gamma, dx=None):
+    rows, C = x.shape
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty_like(x)
+    check(lib().b200lmd_layernorm_bwd_f16(ptr(dy), ptr(x), ptr(stats), ptr(gamma), ptr(dx), ctypes.c_longlong(rows),
+                                          _i(C), _i(int(acc)), cur_stream()))
+    return dx
+
+
+def geglu_bwd(pre, dy):
+    rows, F = dy.shape
+    dpre = torch.empty_like(pre)
+    check(lib().b200lmd_geglu_bwd_f16(ptr(pre), ptr(dy), ptr(dpre), ctypes.c_longlong(rows), _i(F), cur_stream()))
+    return dpre
