@@ -55,12 +55,68 @@ int b200lmd_project_heads_f16(const void* x, int ldx, const void* w, int M, int 
                               int head_dim, int which0, void* q, int q_alloc, void* k, int k_alloc, void* vt,
                               int v_alloc, void* stream);
 
+/* General form: for projection i in {0,1,2} (relative to which0) write a row-major slab rm[i] [B*heads, rm_alloc[i],
+ * dp] and/or a transposed slab tr[i] [B*heads, d16, tr_alloc[i]] (NULL = skip).  The backward kernels consume
+ * row-major Q,K,V,dO and transposed Q^T,K^T,dO^T. */
+int b200lmd_project_heads2_f16(const void* x, int ldx, const void* w, int M, int N, int K, int rows_per_img, int heads,
+                               int head_dim, int which0, void* const* rm, const int* rm_alloc, void* const* tr,
+                               const int* tr_alloc, void* stream);
+
+/* Attention backward (activations only; weights are frozen): replaces torch.autograd through the attention of
+ * models/attention_processor.py:216-233,447 inside torch.autograd.grad at models/pipelines.py:56.
+ *   dq [B*nq, ld_dq], dk/dv [B*nk_store, ld] (NULL = not needed, e.g. text K/V are constants)
+ *   delta: fp32 scratch [B*heads, q_alloc] (= rowsum(dO*O), computed here from the token-major o_tok/do_tok);
+ *          pass NULL with a single KV tile to have it formed in-kernel (needed when dp_extra is given)
+ *   dp_extra: optional fp32 [B*heads, nq, ext_ld] added to dP (the guidance loss's d loss / d P)
+ *   dO may be NULL (no downstream gradient: last guidance layer), then only dp_extra drives dq. */
+int b200lmd_attention_bwd_f16(const void* q, const void* k, const void* v, const void* dO, const void* qt,
+                              const void* kt, const void* dOt, const void* lse2, void* delta, const void* o_tok,
+                              int ld_o, const void* do_tok, int ld_do, const void* dp_extra, int ext_ld, void* dq,
+                              int ld_dq, void* dk, int ld_dk, void* dv, int ld_dv, int nk_store, int B, int heads,
+                              int nq, int nk, int q_alloc, int k_alloc, int head_dim, float scale, void* stream);
+
 /* softmax(scale * q k^T) v over the slabs above -> out[B*nq, ldo] (head h at columns h*d..), lse2 (optional, fp32
  * [B*heads, q_alloc], log2-domain row statistic kept for the backward).  Replaces F.scaled_dot_product_attention at
  * models/attention_processor.py:355 and the baddbmm/softmax/bmm path :216-233,447 when no map is requested. */
 int b200lmd_attention_fwd_f16(const void* q, const void* k, const void* vt, void* out, int ldo, void* lse2, int B,
                               int heads, int nq, int nk, int q_alloc, int k_alloc, int head_dim, float scale,
                               void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fused cross-attention + loss
+ * The kernel the north star grades: cross-attention (T <= 128 text keys) with the LMD/LMD+ guidance loss evaluated in
+ * the same launch.  Replaces AttnProcessor.__call__'s explicit path (models/attention_processor.py:407-483: probs,
+ * P.V, save_attn_to_dict / return_token_ca_only) TOGETHER WITH utils/guidance.py:91-286 (compute_ca_lossv3) and the
+ * d loss / d P half of torch.autograd.grad (models/pipelines.py:56).
+ * Loss tables (device memory, built by the host mirror llm-groundeddiffusion_b200/guidance.py):
+ *   terms[img_term_off[b] .. img_term_off[b+1]) for image b; weights already contain loss_scale and the normalisers
+ *   1/(n_tokens * n_objects * n_keys) (utils/guidance.py:146,270) resp. w_ref/(n_boxes*n_tok*n_obj*n_keys*heads)
+ *   (:233-237,284); masks are the scale_proportion rasters (utils/utils.py:57-70) as bytes [n_masks][n].
+ * Outputs: loss_part[B*heads] (sum over heads and keys = loss * loss_scale), dp_extra[B*heads][n][ext_ld] =
+ * gscale * d loss / d P (fed to b200lmd_attention_bwd_f16), optional maps. counters must be zero on first use. */
+typedef struct {
+  int type;            /* 0: fg/bg top-k energy, 1: reference-attention L1 */
+  int slot, mask, k_fg, k_bg;
+  float w_fg, w_bg, w_ref;
+  int ref;
+} b200lmd_loss_term;
+typedef struct {
+  const int* img_term_off;
+  const b200lmd_loss_term* terms;
+  const unsigned char* masks;
+  const float* refs;      /* [n_refs][heads][n] */
+  const int* slot_tok;    /* [B][b200lmd_max_loss_slots()] token index per saved column, -1 terminated */
+  float* pcol;            /* scratch [B*heads][slots][n] */
+  int* counters;          /* [B*heads] */
+  float* loss_part;       /* [B*heads] */
+  float* dp_extra;        /* [B*heads][n][ext_ld] */
+  int ext_ld;
+  float gscale;
+  float eps;              /* 1e-5 (utils/guidance.py:150) */
+} b200lmd_xattn_loss;
+int b200lmd_max_loss_slots(void);
+int b200lmd_xattn_fwd_f16(const void* q, const void* k, const void* vt, void* out, int ldo, void* lse2, void* probs,
+                          const int* save_tok, void* probs_tok, const b200lmd_xattn_loss* loss, int B, int heads,
+                          int nq, int nk, int q_alloc, int k_alloc, int head_dim, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ normalisation
  * GroupNorm (+ optional SiLU) over NHWC fp16 x[B, n, C]: stats then apply (torch.nn.GroupNorm inside diffusers

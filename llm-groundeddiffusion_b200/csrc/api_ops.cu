@@ -127,6 +127,58 @@ extern "C" int b200lmd_round_d16(int d) {
   try { return round_d16(d); } catch (...) { return -1; }
 }
 
+extern "C" int b200lmd_project_heads2_f16(const void* x, int ldx, const void* w, int M, int N, int K,
+                                          int rows_per_img, int heads, int head_dim, int which0, void* const* rm,
+                                          const int* rm_alloc, void* const* tr, const int* tr_alloc, void* stream) {
+  return guarded([&] {
+    if (head_dim % 8) throw std::runtime_error("head_dim must be a multiple of 8");
+    GemmBuild b;
+    b.A = (const __half*)x; b.aW = M; b.a_ld = ldx; b.Cin = K;
+    b.Wt = (const __half*)w; b.N = N;
+    b.gW = M;
+    b.taps[0] = GemmTap{0, 0, 0, 0};
+    GemmParams ep = default_epilogue();
+    ep.mode = EPI_HEADS;
+    ep.rows_per_img = rows_per_img;
+    ep.C = heads * head_dim; ep.heads = heads; ep.d = head_dim; ep.which0 = which0;
+    ep.dp = round_dp(head_dim); ep.d16 = round_d16(head_dim);
+    for (int i = 0; i < 3; ++i) {
+      ep.rm[i] = (__half*)rm[i]; ep.rm_alloc[i] = rm_alloc[i];
+      ep.tr[i] = (__half*)tr[i]; ep.tr_alloc[i] = tr_alloc[i];
+    }
+    ep.OH = 1; ep.OW = M;
+    run_gemm(build_gemm(b, ep), (cudaStream_t)stream);
+  });
+}
+
+extern "C" int b200lmd_attention_bwd_f16(const void* q, const void* k, const void* v, const void* dO, const void* qt,
+                                         const void* kt, const void* dOt, const void* lse2, void* delta,
+                                         const void* o_tok, int ld_o, const void* do_tok, int ld_do,
+                                         const void* dp_extra, int ext_ld, void* dq, int ld_dq, void* dk, int ld_dk,
+                                         void* dv, int ld_dv, int nk_store, int B, int heads, int nq, int nk,
+                                         int q_alloc, int k_alloc, int head_dim, float scale, void* stream) {
+  return guarded([&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* dl = nullptr;
+    if (delta) {
+      run_attn_delta((const __half*)do_tok, ld_do, (const __half*)o_tok, ld_o, (float*)delta, B, heads, nq, q_alloc,
+                     head_dim, st);
+      dl = (const float*)delta;
+    }
+    run_attn_dq(build_attn_dq((const __half*)q, (const __half*)dO, (const __half*)k, (const __half*)v,
+                              (const __half*)kt, (const float*)lse2, dl, (const float*)dp_extra, ext_ld, (__half*)dq,
+                              ld_dq, B, heads, nq, nk, q_alloc, k_alloc, head_dim, scale),
+                st);
+    if (dk || dv) {
+      if (!dl) throw std::runtime_error("dK/dV need the delta buffer");
+      run_attn_dkv(build_attn_dkv((const __half*)k, (const __half*)v, (const __half*)q, (const __half*)dO,
+                                  (const __half*)qt, (const __half*)dOt, (const float*)lse2, dl, (__half*)dk, ld_dk,
+                                  (__half*)dv, ld_dv, nk_store, B, heads, nq, nk, q_alloc, k_alloc, head_dim, scale),
+                   st);
+    }
+  });
+}
+
 extern "C" int b200lmd_project_heads_f16(const void* x, int ldx, const void* w, int M, int N, int K, int rows_per_img,
                                          int heads, int head_dim, int which0, void* q, int q_alloc, void* k,
                                          int k_alloc, void* vt, int v_alloc, void* stream) {
@@ -225,3 +277,4 @@ extern "C" int b200lmd_geglu_bwd_f16(const void* pre, const void* dy, void* dpre
     B200_CHECK(cudaGetLastError());
   });
 }
+#include "api_xattn.cuh"

@@ -69,6 +69,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qt = blockIdx.x;
   const int bh = blockIdx.y;
   const int nkv = (p.nk + KVT - 1) / KVT;
+  // without a precomputed delta the KV tiles are walked twice: pass A reduces delta = sum_k P*dP, pass B forms dS
+  const int first_b = p.delta ? 0 : nkv;
+  const int total = first_b + nkv;
 
   if (warp == 1) {
     if (elect_one()) {
@@ -102,7 +105,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < nkv; ++j) {
+      for (int it = 0; it < total; ++it) {
+        const int j = it % nkv;
         mbar_wait(&kv_empty[stage], phase ^ 1);
         uint8_t* sK = sStage + stage * Cfg::STAGE_BYTES;
         uint8_t* sV = sK + Cfg::K_BYTES;
@@ -123,9 +127,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(q_full, 0);
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < nkv; ++j) {
+    for (int it = 0; it < total; ++it) {
+      const bool pass_b = it >= first_b;
+      const int j = it - first_b;  // tile index inside pass B
       mbar_wait(&kv_full[stage], phase);
-      mbar_wait(sdp_empty, (j & 1) ^ 1);
+      mbar_wait(sdp_empty, (it & 1) ^ 1);
       tc_fence_after();
       const uint32_t kaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES);
       const uint32_t vaddr = kaddr + Cfg::K_BYTES;
@@ -148,23 +154,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
         tc_commit(sdp_full);
+        if (!pass_b) tc_commit(&kv_empty[stage]);  // pass A: the stage is free once S / dP exist
       }
       __syncwarp();
-      mbar_wait(ds_full, j & 1);
-      tc_fence_after();
-      if (elect_one()) {
+      if (pass_b) {
+        mbar_wait(ds_full, j & 1);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int a = 0; a < KVT / 64; ++a) {
-          const uint64_t sd = make_desc_k_sw128(smem_u32(sdS) + a * 16384);
-          const uint64_t td = make_desc_k_sw128(ktaddr + a * Cfg::KT_ATOM);
+          for (int a = 0; a < KVT / 64; ++a) {
+            const uint64_t sd = make_desc_k_sw128(smem_u32(sdS) + a * 16384);
+            const uint64_t td = make_desc_k_sw128(ktaddr + a * Cfg::KT_ATOM);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tdQ, sd + k * 2, td + k * 2, idesc_q, (j | a | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tdQ, sd + k * 2, td + k * 2, idesc_q, (j | a | k) ? 1u : 0u);
+          }
+          tc_commit(&kv_empty[stage]);
+          tc_commit(ds_empty);
+          if (j == nkv - 1) tc_commit(dq_full);
         }
-        tc_commit(&kv_empty[stage]);
-        tc_commit(ds_empty);
-        if (j == nkv - 1) tc_commit(dq_full);
+        __syncwarp();
       }
-      __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
@@ -175,13 +184,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool ok = qrow < p.nq;
     const float L2 = ok ? p.lse2[(long long)bh * p.nq_alloc + qrow] : 0.f;
     const float* ext = (p.extra && ok) ? p.extra + ((long long)bh * p.nq + qrow) * p.ext_ld : nullptr;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(sdp_full, j & 1);
+    float delta = (p.delta && ok) ? p.delta[(long long)bh * p.nq_alloc + qrow] : 0.f;
+    for (int it = 0; it < total; ++it) {
+      const bool pass_b = it >= first_b;
+      const int j = it - first_b;
+      mbar_wait(sdp_full, it & 1);
       tc_fence_after();
-      const int kbase = j * KVT;
-      float delta = (p.delta && ok) ? p.delta[(long long)bh * p.nq_alloc + qrow] : 0.f;
-      if (!p.delta) {
-        // single KV tile: delta = sum_k P * dP_total
+      const int kbase = (it % nkv) * KVT;
+      if (!pass_b) {
+        // pass A: delta += sum_k P * dP_total over this tile
 #pragma unroll 1
         for (int c0 = 0; c0 < KVT; c0 += 32) {
           uint32_t s[32], g[32];
@@ -199,6 +210,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(sdp_empty);
+        continue;
       }
       mbar_wait(ds_empty, (j & 1) ^ 1);
 #pragma unroll 1
@@ -337,7 +352,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tST = tmem_base, tdPT = tmem_base + QT, tdV = tmem_base + 2 * QT, tdK = tmem_base + 2 * QT + D16;
+  constexpr int D64 = (D16 + 63) / 64 * 64;
+  const uint32_t tST = tmem_base, tdPT = tmem_base + QT, tdV = tmem_base + 2 * QT, tdK = tmem_base + 2 * QT + D64;
+  static_assert(2 * QT + D64 + D16 <= 512, "TMEM budget");
 
   if (warp == 0) {
     if (elect_one()) {

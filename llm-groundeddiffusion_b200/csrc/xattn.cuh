@@ -1,0 +1,361 @@
+// Fused cross-attention + layout-guidance loss (forward), sm_100a.
+//
+// One CTA = 128 query rows of one (image, head).  The text has T <= 128 keys, so the whole row of scores is one tcgen05
+// tile: S = Q K^T (TMEM) -> softmax by one thread per row -> fp16 P to shared memory (A operand) -> O = P V (TMEM) ->
+// O to HBM.  In the same kernel:
+//   * requested attention maps leave as fp16 (full [BH, n, T] and/or one token column per image) - the reference's
+//     save_attn_to_dict / return_token_ca_only contract (models/attention_processor.py:463-482);
+//   * the columns of P that the guidance loss reads go to a small fp32 scratch; the LAST CTA of each (image, head)
+//     to arrive (atomic ticket) evaluates the per-phrase top-k foreground/background energies and the
+//     reference-attention L1 terms (utils/guidance.py:91-242) with warp/CTA reductions, writes the loss partial and
+//     d(loss)/dP (consumed as dP_extra by attn_bwd_dq_kernel), so neither the maps nor an autograd graph exist.
+// Loss tables are built on the host (llm-groundeddiffusion_b200/guidance.py) and restate scale_proportion / k_fg /
+// k_bg / normalisers exactly (integers must match the reference bit for bit).
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kMaxSlots = 48;
+
+struct LossTerm {
+  int type;     // 0 = energy (fg/bg top-k), 1 = reference-attention L1
+  int slot;     // which saved column of P
+  int mask;     // mask id (row of `masks`)
+  int k_fg, k_bg;
+  float w_fg, w_bg;   // already include loss_scale and all normalisers (per head)
+  float w_ref;
+  int ref;      // ref-map id (row block of `refs`)
+};
+
+struct XattnLoss {
+  const int* img_term_off;   // [B+1]
+  const LossTerm* terms;
+  const uint8_t* masks;      // [n_masks][n]
+  const float* refs;         // [n_refs][heads][n]
+  const int* slot_tok;       // [B][kMaxSlots], -1 = unused
+  float* pcol;               // [BH][kMaxSlots][n]
+  int* counters;             // [BH], zero on entry, self-resetting
+  float* loss_part;          // [BH]
+  float* dp_extra;           // [BH][n][ext_ld]
+  int ext_ld;
+  float gscale;
+  float eps;
+};
+
+struct XattnParams {
+  int heads, nq, nk;
+  int nq_alloc, nk_alloc;
+  int d;
+  float scale_log2;
+  __half* out; int ldo;
+  float* lse2;               // [BH, nq_alloc] or null
+  __half* probs;             // [BH, nq, nk] or null
+  const int* save_tok;       // [B] token index per image (or null); column goes to probs_tok
+  __half* probs_tok;         // [BH, nq]
+  int has_loss;
+  XattnLoss L;
+};
+
+template <int DPB, int D16>
+struct XattnCfg {
+  static constexpr int Q_BYTES = DPB * 16384;
+  static constexpr int V_ATOM = D16 * 128;
+  static constexpr int P_BYTES = 2 * 16384;
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * V_ATOM + P_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ float block128_sum(float v, float* red, int tid) {
+  // reduction over the 128 softmax threads (4 warps); red: >= 4 floats of shared scratch
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+template <int DPB, int D16>
+__global__ void __launch_bounds__(192, 1)
+xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ XattnParams p) {
+  using Cfg = XattnCfg<DPB, D16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::Q_BYTES;
+  uint8_t* sP = sV + 2 * Cfg::V_ATOM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* ld_full = bars;
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_full = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
+  float* s_red = reinterpret_cast<float*>(s_flag + 1);  // 4 floats
+
+  const int warp = threadIdx.x >> 5;
+  const int qt = blockIdx.x;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads, h = bh % p.heads;
+
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(ld_full, 1);
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 4);
+      mbar_init(o_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(ld_full, 2 * Cfg::Q_BYTES + 2 * Cfg::V_ATOM);
+      for (int a = 0; a < DPB; ++a) {
+        tma_load_3d(sQ + a * 16384, &tmQ, ld_full, a * 64, qt * 128, bh);
+        tma_load_3d(sK + a * 16384, &tmK, ld_full, a * 64, 0, bh);
+      }
+      for (int a = 0; a < 2; ++a) tma_load_3d(sV + a * Cfg::V_ATOM, &tmVt, ld_full, a * 64, 0, bh);
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, D16);
+    mbar_wait(ld_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int a = 0; a < DPB; ++a) {
+        const uint64_t ad = make_desc_k_sw128(smem_u32(sQ) + a * 16384);
+        const uint64_t bd = make_desc_k_sw128(smem_u32(sK) + a * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tS, ad + k * 2, bd + k * 2, idesc_s, (a | k) ? 1u : 0u);
+      }
+      tc_commit(s_full);
+    }
+    __syncwarp();
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const uint64_t ad = make_desc_k_sw128(smem_u32(sP) + a * 16384);
+        const uint64_t bd = make_desc_k_sw128(smem_u32(sV) + a * Cfg::V_ATOM);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tO, ad + k * 2, bd + k * 2, idesc_o, (a | k) ? 1u : 0u);
+      }
+      tc_commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane_id();
+    const int tid = threadIdx.x - 64;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int qrow = qt * 128 + r;
+    const bool ok = qrow < p.nq;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      if (c0 >= p.nk) break;
+      uint32_t v[32];
+      tmem_ld_x32(tS + lane_off + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < p.nk) m = fmaxf(m, __uint_as_float(v[i]));
+    }
+    m *= p.scale_log2;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      if (c0 >= p.nk) break;
+      uint32_t v[32];
+      tmem_ld_x32(tS + lane_off + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < p.nk) l += exp2f(__uint_as_float(v[i]) * p.scale_log2 - m);
+    }
+    const float inv_l = 1.f / l;
+    __half* prow = (p.probs && ok) ? p.probs + ((long long)bh * p.nq + qrow) * p.nk : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t pk[16];
+      if (c0 < p.nk) {
+        uint32_t v[32];
+        tmem_ld_x32(tS + lane_off + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = (c0 + 2 * i < p.nk) ? exp2f(__uint_as_float(v[2 * i]) * p.scale_log2 - m) * inv_l : 0.f;
+          const float bb = (c0 + 2 * i + 1 < p.nk) ? exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m) * inv_l : 0.f;
+          pk[i] = pack_h2(a, bb);
+        }
+        if (prow) {
+          const __half* hp = reinterpret_cast<const __half*>(pk);
+          for (int i = 0; i < 32 && c0 + i < p.nk; ++i) prow[c0 + i] = hp[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      }
+      uint8_t* atom = sP + (c0 >> 6) * 16384;
+      const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0 + q)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+    // columns of P needed outside: read back this thread's own row from shared memory
+    auto p_at = [&](int tok) -> float {
+      const uint8_t* atom = sP + (tok >> 6) * 16384;
+      const __half* chunk = reinterpret_cast<const __half*>(atom + sw128_offset(r, (tok & 63) >> 3));
+      return __half2float(chunk[tok & 7]);
+    };
+    if (ok && p.save_tok) {
+      const int tok = p.save_tok[b];
+      if (tok >= 0) p.probs_tok[(long long)bh * p.nq + qrow] = __float2half_rn(p_at(tok));
+    }
+    if (ok && p.has_loss) {
+      for (int s = 0; s < kMaxSlots; ++s) {
+        const int tok = p.L.slot_tok[b * kMaxSlots + s];
+        if (tok < 0) break;
+        p.L.pcol[((long long)bh * kMaxSlots + s) * p.nq + qrow] = p_at(tok);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(p_full);
+
+    // ---------------- O epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    __half* orow = p.out + ((long long)b * p.nq + qrow) * p.ldo + h * p.d;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D16; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tO + lane_off + c0, v);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (c0 + g * 8 < p.d) {
+            uint4 st;
+            st.x = pack_h2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+            st.y = pack_h2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+            st.z = pack_h2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+            st.w = pack_h2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = st;
+          }
+      }
+    }
+    if (ok && p.lse2) p.lse2[(long long)bh * p.nq_alloc + qrow] = m + log2f(l);
+    tc_fence_before();
+
+    // ---------------- guidance loss: last CTA of this (image, head) reduces
+    if (p.has_loss) {
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        const int tiles = gridDim.x;
+        const int old = atomicAdd(&p.L.counters[bh], 1);
+        *s_flag = (old == tiles - 1);
+        if (old == tiles - 1) p.L.counters[bh] = 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_flag) {
+        __threadfence();
+        const int n = p.nq;
+        float* col = reinterpret_cast<float*>(sP);   // P tile is dead: reuse as [n] values + [n] masked values
+        float* val = col + n;                        // n <= 4096 fits (32 KB)
+        float* dpx = p.L.dp_extra + (long long)bh * n * p.L.ext_ld;
+        for (int i = tid; i < n * p.L.ext_ld; i += 128) dpx[i] = 0.f;
+        float loss_acc = 0.f;
+        const int t0 = p.L.img_term_off[b], t1 = p.L.img_term_off[b + 1];
+        for (int t = t0; t < t1; ++t) {
+          const LossTerm T = p.L.terms[t];
+          const int tok = p.L.slot_tok[b * kMaxSlots + T.slot];
+          const float* src = p.L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
+          const uint8_t* mk = p.L.masks + (long long)T.mask * n;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = tid; i < n; i += 128) col[i] = __ldcg(src + i);
+          if (T.type == 0) {
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+              const int k = side ? T.k_bg : T.k_fg;
+              const float w = side ? T.w_bg : T.w_fg;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              for (int i = tid; i < n; i += 128) val[i] = (mk[i] != 0) == (side == 0) ? col[i] : 0.f;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              float part = 0.f;
+              for (int i = tid; i < n; i += 128) {
+                const float vi = val[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                  const float vj = val[j];
+                  rank += (vj > vi) || (vj == vi && j < i);
+                }
+                if (rank < k) {
+                  part += vi;
+                  const bool inside = (mk[i] != 0) == (side == 0);
+                  if (inside) dpx[(long long)i * p.L.ext_ld + tok] += (side ? w : -w) / (float)k * p.L.gscale;
+                }
+              }
+              const float tot = block128_sum(part, s_red, tid);
+              loss_acc += side ? w * tot / (float)k : w * (1.f - tot / (float)k);
+            }
+          } else {
+            const float* R = p.L.refs + ((long long)T.ref * p.heads + h) * n;
+            float sa = 0.f, sr = 0.f;
+            for (int i = tid; i < n; i += 128)
+              if (mk[i]) {
+                sa += col[i];
+                sr += R[i];
+              }
+            const float A = block128_sum(sa, s_red, tid) + p.L.eps;
+            const float Rs = block128_sum(sr, s_red, tid) + p.L.eps;
+            float l1 = 0.f, inner = 0.f;
+            for (int i = tid; i < n; i += 128)
+              if (mk[i]) {
+                const float ah = col[i] / A, rh = R[i] / Rs;
+                const float df = ah - rh;
+                const float sg = (df > 0.f) - (df < 0.f);
+                l1 += fabsf(df);
+                inner += sg * ah;
+              }
+            const float L1 = block128_sum(l1, s_red, tid);
+            const float In = block128_sum(inner, s_red, tid);
+            loss_acc += T.w_ref * L1;
+            for (int i = tid; i < n; i += 128)
+              if (mk[i]) {
+                const float ah = col[i] / A, rh = R[i] / Rs;
+                const float df = ah - rh;
+                const float sg = (df > 0.f) - (df < 0.f);
+                dpx[(long long)i * p.L.ext_ld + tok] += T.w_ref / A * (sg - In) * p.L.gscale;
+              }
+          }
+        }
+        if (tid == 0) p.L.loss_part[bh] = loss_acc;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace b200

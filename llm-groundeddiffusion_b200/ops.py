@@ -134,3 +134,35 @@ def geglu_bwd(pre, dy):
     dpre = torch.empty_like(pre)
     check(lib().b200lmd_geglu_bwd_f16(ptr(pre), ptr(dy), ptr(dpre), ctypes.c_longlong(rows), _i(F), cur_stream()))
     return dpre
+
+
+def project_heads2(x, w, rows_per_img, heads, d, which0, rm=(None, None, None), tr=(None, None, None)):
+    """general head-split projection: rm[i] [BH, alloc, dp] row-major, tr[i] [BH, d16, alloc] transposed"""
+    M, K = x.shape
+    N = w.shape[0]
+    VP = ctypes.c_void_p * 3
+    IP = ctypes.c_int * 3
+    rmp = VP(*[t.data_ptr() if t is not None else None for t in rm])
+    trp = VP(*[t.data_ptr() if t is not None else None for t in tr])
+    rma = IP(*[t.shape[1] if t is not None else 0 for t in rm])
+    tra = IP(*[t.shape[2] if t is not None else 0 for t in tr])
+    check(lib().b200lmd_project_heads2_f16(ptr(x), _i(x.stride(0)), ptr(w), _i(M), _i(N), _i(K), _i(rows_per_img),
+                                           _i(heads), _i(d), _i(which0), rmp, rma, trp, tra, cur_stream()))
+
+
+def attention_bwd(q, k, v, dO, qt, kt, dOt, lse2, o_tok, do_tok, B, heads, nq, nk, d, scale, dp_extra=None,
+                  want_dkv=True, nk_store=None, use_delta=True):
+    C = heads * d
+    nk_store = nk if nk_store is None else nk_store
+    dq = torch.zeros(B * nq, C, device=q.device, dtype=torch.float16)
+    dk = torch.zeros(B * nk_store, C, device=q.device, dtype=torch.float16) if want_dkv else None
+    dv = torch.zeros(B * nk_store, C, device=q.device, dtype=torch.float16) if want_dkv else None
+    delta = torch.zeros(B * heads, q.shape[1], device=q.device, dtype=torch.float32) if use_delta else None
+    check(lib().b200lmd_attention_bwd_f16(
+        ptr(q), ptr(k), ptr(v), ptr(dO), ptr(qt), ptr(kt), ptr(dOt), ptr(lse2), ptr(delta), ptr(o_tok),
+        _i(o_tok.stride(0) if o_tok is not None else 0), ptr(do_tok),
+        _i(do_tok.stride(0) if do_tok is not None else 0), ptr(dp_extra),
+        _i(dp_extra.shape[2] if dp_extra is not None else 0), ptr(dq), _i(C), ptr(dk), _i(C), ptr(dv), _i(C),
+        _i(nk_store), _i(B), _i(heads), _i(nq), _i(nk), _i(q.shape[1]), _i(k.shape[1]), _i(d), _f(scale),
+        cur_stream()))
+    return dq, dk, dv
