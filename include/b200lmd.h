@@ -41,6 +41,60 @@ int b200lmd_linear_geglu_f16(const void* x, int ldx, const void* w_il, const voi
 int b200lmd_conv3x3_f16(const void* x, const void* w, const void* bias, const void* chan_add, const void* residual,
                         void* y, void* y_f32, int B, int H, int W, int Cin, int Cout, void* stream);
 
+/* Descriptor form of the implicit GEMM behind every op above:
+ *   D[m, n] = sum_{tap, c} A[pixel(m) + off(tap), c] * W[n, wtap(tap), c]
+ * A is NHWC fp16 [aB, aH, aW, a_ld] (channels [0, Cin) are contracted); the output-pixel grid [gB, gH, gW] is walked in
+ * 128-pixel bricks, input pixel = output pixel + (dx, dy, db) in A's coordinates with zero fill outside, which covers
+ * stride-1 convs directly, stride-2 convs over a space-to-depth copy (b200lmd_space_to_depth_f16: sub-image
+ * (py*2+px)*B+b) and transposed (dgrad) convs via the output mapping out_row = ((b*OH + y*sy+oy)*OW + x*sx+ox).
+ * W is fp16 [N][wtaps][Cin].  mode: 0 row-major out (bias, chan_add[B,N], residual, fp16/fp32 out, accumulate),
+ * 1 GEGLU, 2 head-split slabs.  Replaces every nn.Conv2d / nn.Linear of the UNet (models/unet_2d_condition.py:289,
+ * 567; diffusers resnet.py conv1/conv2/conv_shortcut/Downsample2D/Upsample2D) and, with pre-transposed weights, the
+ * activation gradients autograd computes for them (models/pipelines.py:56). */
+typedef struct {
+  const void* A; int aB, aH, aW, a_ld, Cin;
+  const void* W; int N, wtaps;
+  int gB, gH, gW;
+  int ntaps; short taps[9][4];   /* dx, dy, db, wtap */
+  int OH, OW, sy, sx, oy, ox;
+  int mode; float alpha;
+  const void* bias; const void* chan_add; int rows_per_img;
+  const void* residual; int ldr;
+  void* out; int ldo; void* out_f32; int ldo32; int accumulate; void* pre;
+  int heads, head_dim, which0;
+  void* rm[3]; int rm_alloc[3]; void* tr[3]; int tr_alloc[3];
+} b200lmd_gemm_desc;
+int b200lmd_gemm(const b200lmd_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ layout / schedule helpers
+ * HBM-bound, vectorised; each replaces a torch op on the reference path:
+ *   copy_cols   torch.cat(dim=1) of skip connections (models/unet_2d_blocks.py:648,767) and its split adjoint
+ *   copy_rows   torch.cat([x, objs], dim=1) / [:, :n_visual] of the GLIGEN fuser (models/attention.py:50) + gating
+ *   upsample2x  F.interpolate(scale_factor=2, nearest) in diffusers Upsample2D, and its adjoint
+ *   pack_latents / unpack_grad   NCHW fp32 latents <-> NHWC-8 fp16 activations (CFG duplicates with rep=2,
+ *                                models/pipelines.py:420)
+ *   timestep_embed  diffusers Timesteps(flip_sin_to_cos=True, freq_shift=0); silu_f32_to_f16 the MLP activation
+ *   cfg_ddim_blend  eps_u + s(eps_c - eps_u), DDIM eta=0 step, frozen blend (models/pipelines.py:436-446)
+ *   latent_update   z -= sqrt(1 - alpha_bar_t) * grad for still-active images (models/pipelines.py:62-69) */
+int b200lmd_copy_cols_f16(const void* src, int ld_src, int src_off, void* dst, int ld_dst, int dst_off, long long rows,
+                          int ncols, int accumulate, void* stream);
+int b200lmd_copy_rows_f16(const void* src, int rows_per_img_src, int src_row0, void* dst, int rows_per_img_dst,
+                          int dst_row0, int B, int nrows, int C, float alpha, int accumulate, void* stream);
+int b200lmd_upsample2x_f16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int b200lmd_upsample2x_bwd_f16(const void* dy, void* dx, int B, int H, int W, int C, int accumulate, void* stream);
+int b200lmd_space_to_depth_f16(const void* x, void* y, int B, int Hout, int Wout, int C, void* stream);
+int b200lmd_pack_latents(const void* z_f32, void* y_f16, int B, int Cz, int HW, int rep, void* stream);
+int b200lmd_unpack_grad(const void* g_f32, int ld, void* out_f32, int B, int Cz, int HW, float scale, void* stream);
+int b200lmd_timestep_embed(const void* t_f32, void* y_f16, int B, int dim, void* stream);
+int b200lmd_silu_f32_to_f16(const void* x, void* y, long long n, void* stream);
+int b200lmd_cfg_ddim_blend(void* z, const void* eps, int ld_eps, int B, int Cz, int HW, float guidance_scale,
+                           float sa_t, float sb_t, float sa_p, float sb_p, int v_pred, const void* frozen,
+                           const void* mask, void* stream);
+int b200lmd_latent_update(void* z, const void* grad, int ld_g, int B, int Cz, int HW, float step_scale,
+                          float inv_gscale, const int* active, void* stream);
+int b200lmd_attn_delta_slab(const void* dO_slab, const void* o_tok, int ld_o, void* delta, int B, int heads, int nq,
+                            int q_alloc, int head_dim, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ attention
  * Head-split projection: [M, nproj*C] = x[M,K] . W[nproj*C, K]^T scattered into per-head operand slabs
  * (to_q / to_k / to_v of models/attention_processor.py:426-438 plus head_to_batch_dim :190-199 in one pass):

@@ -1,0 +1,162 @@
+// C-ABI: descriptor-driven implicit GEMM (every conv / linear / dgrad variant) and the HBM-bound helper kernels.
+// Included by api_ops.cu.
+#pragma once
+
+extern "C" int b200lmd_gemm(const b200lmd_gemm_desc* d, void* stream) {
+  return b200::guarded([&] {
+    using namespace b200;
+    GemmBuild b;
+    b.A = (const __half*)d->A; b.aB = d->aB; b.aH = d->aH; b.aW = d->aW; b.a_ld = d->a_ld; b.Cin = d->Cin;
+    b.Wt = (const __half*)d->W; b.N = d->N; b.wtaps = d->wtaps;
+    b.gB = d->gB; b.gH = d->gH; b.gW = d->gW;
+    b.ntaps = d->ntaps;
+    if (d->ntaps < 1 || d->ntaps > 9) throw std::runtime_error("gemm: ntaps out of range");
+    for (int i = 0; i < d->ntaps; ++i) b.taps[i] = GemmTap{d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]};
+    GemmParams ep = default_epilogue();
+    ep.OH = d->OH; ep.OW = d->OW; ep.sy = d->sy; ep.sx = d->sx; ep.oy = d->oy; ep.ox = d->ox;
+    ep.mode = d->mode; ep.alpha = d->alpha;
+    ep.bias = (const float*)d->bias; ep.chan_add = (const float*)d->chan_add; ep.rows_per_img = d->rows_per_img;
+    ep.residual = (const __half*)d->residual; ep.ldr = d->ldr;
+    ep.out = (__half*)d->out; ep.ldo = d->ldo; ep.out_f32 = (float*)d->out_f32; ep.ldo32 = d->ldo32;
+    ep.accumulate_out = d->accumulate; ep.pre = (__half*)d->pre;
+    if (d->mode == EPI_HEADS) {
+      if (d->head_dim % 8) throw std::runtime_error("head_dim must be a multiple of 8");
+      ep.C = d->heads * d->head_dim; ep.heads = d->heads; ep.d = d->head_dim; ep.which0 = d->which0;
+      ep.dp = round_dp(d->head_dim); ep.d16 = round_d16(d->head_dim);
+      for (int i = 0; i < 3; ++i) {
+        ep.rm[i] = (__half*)d->rm[i]; ep.rm_alloc[i] = d->rm_alloc[i];
+        ep.tr[i] = (__half*)d->tr[i]; ep.tr_alloc[i] = d->tr_alloc[i];
+      }
+    }
+    if (d->Cin % 8 || d->a_ld % 8) throw std::runtime_error("gemm: channel counts must be multiples of 8");
+    run_gemm(build_gemm(b, ep), (cudaStream_t)stream);
+  });
+}
+
+#define B200_EW(call)                                   \
+  return b200::guarded([&] {                            \
+    using namespace b200;                               \
+    cudaStream_t st = (cudaStream_t)stream;             \
+    call;                                               \
+    B200_CHECK(cudaGetLastError());                     \
+  })
+
+extern "C" int b200lmd_copy_cols_f16(const void* src, int ld_src, int src_off, void* dst, int ld_dst, int dst_off,
+                                     long long rows, int ncols, int accumulate, void* stream) {
+  B200_EW((copy_cols_kernel<<<ew_grid(rows * (ncols / 8)), 256, 0, st>>>((const __half*)src, ld_src, src_off,
+                                                                         (__half*)dst, ld_dst, dst_off, rows, ncols,
+                                                                         accumulate)));
+}
+
+namespace b200 {
+// dst[b*rd + dst_row0 + i, :] (+)= alpha * src[b*rs + src_row0 + i, :]  for i < nrows   (fp16, C % 8 == 0)
+__global__ void copy_rows_kernel(const __half* __restrict__ src, int rs, int src_row0, __half* __restrict__ dst, int rd,
+                                 int dst_row0, int B, int nrows, int C, float alpha, int accumulate) {
+  const int vecs = C >> 3;
+  const long long total = (long long)B * nrows * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    const long long r = i / vecs;
+    const int b = (int)(r / nrows), k = (int)(r % nrows);
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(src + ((long long)b * rs + src_row0 + k) * C + v * 8), f);
+    uint4* d = reinterpret_cast<uint4*>(dst + ((long long)b * rd + dst_row0 + k) * C + v * 8);
+    if (accumulate) {
+      float o[8];
+      unpack8(*d, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = o[j] + alpha * f[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= alpha;
+    }
+    *d = pack8(f);
+  }
+}
+// grad fp32 NHWC [B, HW, ld] -> fp32 NCHW [B, Cz, HW] scaled
+__global__ void unpack_grad_kernel(const float* __restrict__ g, int ld, float* __restrict__ out, int B, int Cz, int HW,
+                                   float scale) {
+  const long long total = (long long)B * Cz * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % Cz);
+    const int b = (int)(i / ((long long)HW * Cz));
+    out[i] = g[((long long)b * HW + p) * ld + c] * scale;
+  }
+}
+// delta[bh, q] from the row-major dO slab [BH, nq_alloc, dp] and token-major O [B*nq, ld]
+__global__ void attn_delta_slab_kernel(const __half* __restrict__ dO, int dp, const __half* __restrict__ O, int ld_o,
+                                       float* __restrict__ delta, int B, int heads, int nq, int nq_alloc, int d) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * heads * nq;
+  for (long long w = blockIdx.x * (long long)warps + (threadIdx.x >> 5); w < total; w += (long long)gridDim.x * warps) {
+    const int q = (int)(w % nq);
+    const long long bh = w / nq;
+    const int b = (int)(bh / heads), h = (int)(bh % heads);
+    float acc = 0.f;
+    for (int j = lane; j < d; j += 32)
+      acc += __half2float(dO[(bh * nq_alloc + q) * dp + j]) * __half2float(O[((long long)b * nq + q) * ld_o + h * d + j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) delta[bh * nq_alloc + q] = acc;
+  }
+}
+}  // namespace b200
+
+extern "C" int b200lmd_copy_rows_f16(const void* src, int rows_per_img_src, int src_row0, void* dst,
+                                     int rows_per_img_dst, int dst_row0, int B, int nrows, int C, float alpha,
+                                     int accumulate, void* stream) {
+  B200_EW((copy_rows_kernel<<<ew_grid((long long)B * nrows * (C / 8)), 256, 0, st>>>(
+      (const __half*)src, rows_per_img_src, src_row0, (__half*)dst, rows_per_img_dst, dst_row0, B, nrows, C, alpha,
+      accumulate)));
+}
+extern "C" int b200lmd_upsample2x_f16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  B200_EW((upsample2x_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 8)), 256, 0, st>>>((const __half*)x, (__half*)y,
+                                                                                         B, H, W, C)));
+}
+extern "C" int b200lmd_upsample2x_bwd_f16(const void* dy, void* dx, int B, int H, int W, int C, int accumulate,
+                                          void* stream) {
+  B200_EW((upsample2x_bwd_kernel<<<ew_grid((long long)B * H * W * (C / 8)), 256, 0, st>>>(
+      (const __half*)dy, (__half*)dx, B, H, W, C, accumulate)));
+}
+extern "C" int b200lmd_space_to_depth_f16(const void* x, void* y, int B, int Hout, int Wout, int C, void* stream) {
+  B200_EW((space_to_depth_kernel<<<ew_grid((long long)4 * B * Hout * Wout * (C / 8)), 256, 0, st>>>(
+      (const __half*)x, (__half*)y, B, Hout, Wout, C)));
+}
+extern "C" int b200lmd_pack_latents(const void* z_f32, void* y_f16, int B, int Cz, int HW, int rep, void* stream) {
+  B200_EW((pack_latents_kernel<<<ew_grid((long long)B * rep * HW), 256, 0, st>>>((const float*)z_f32, (__half*)y_f16, B,
+                                                                                Cz, HW, rep)));
+}
+extern "C" int b200lmd_unpack_grad(const void* g_f32, int ld, void* out_f32, int B, int Cz, int HW, float scale,
+                                   void* stream) {
+  B200_EW((unpack_grad_kernel<<<ew_grid((long long)B * Cz * HW), 256, 0, st>>>((const float*)g_f32, ld, (float*)out_f32,
+                                                                              B, Cz, HW, scale)));
+}
+extern "C" int b200lmd_timestep_embed(const void* t_f32, void* y_f16, int B, int dim, void* stream) {
+  B200_EW((timestep_embed_kernel<<<(B * (dim / 2) + 255) / 256, 256, 0, st>>>((const float*)t_f32, (__half*)y_f16, B,
+                                                                             dim)));
+}
+extern "C" int b200lmd_silu_f32_to_f16(const void* x, void* y, long long n, void* stream) {
+  B200_EW((silu_f32_to_f16_kernel<<<ew_grid(n), 256, 0, st>>>((const float*)x, (__half*)y, n)));
+}
+extern "C" int b200lmd_cfg_ddim_blend(void* z, const void* eps, int ld_eps, int B, int Cz, int HW,
+                                      float guidance_scale, float sa_t, float sb_t, float sa_p, float sb_p,
+                                      int v_pred, const void* frozen, const void* mask, void* stream) {
+  B200_EW((cfg_ddim_blend_kernel<<<ew_grid((long long)B * Cz * HW), 256, 0, st>>>(
+      (float*)z, (const float*)eps, ld_eps, B, Cz, HW, guidance_scale, sa_t, sb_t, sa_p, sb_p, v_pred,
+      (const float*)frozen, (const float*)mask)));
+}
+extern "C" int b200lmd_latent_update(void* z, const void* grad, int ld_g, int B, int Cz, int HW, float step_scale,
+                                     float inv_gscale, const int* active, void* stream) {
+  B200_EW((latent_update_kernel<<<ew_grid((long long)B * Cz * HW), 256, 0, st>>>(
+      (float*)z, (const float*)grad, ld_g, B, Cz, HW, step_scale, inv_gscale, active)));
+}
+extern "C" int b200lmd_attn_delta_slab(const void* dO_slab, const void* o_tok, int ld_o, void* delta, int B, int heads,
+                                       int nq, int q_alloc, int head_dim, void* stream) {
+  B200_EW((attn_delta_slab_kernel<<<ew_grid((long long)B * heads * nq * 32), 256, 0, st>>>(
+      (const __half*)dO_slab, b200::round_dp(head_dim), (const __half*)o_tok, ld_o, (float*)delta, B, heads, nq, q_alloc,
+      head_dim)));
+}

@@ -278,3 +278,4 @@ extern "C" int b200lmd_geglu_bwd_f16(const void* pre, const void* dy, void* dpre
   });
 }
 #include "api_xattn.cuh"
+#include "api_more.cuh"

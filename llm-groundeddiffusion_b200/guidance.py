@@ -1,0 +1,165 @@
+"""Host mirror of the reference's guidance-loss front end (utils/guidance.py, utils/utils.py:57-70).
+
+The arithmetic of the loss runs inside xattn_fwd_kernel (csrc/xattn.cuh); this module only turns the reference's Python
+inputs - bboxes (2- or 3-level lists of normalised xyxy), object_positions (token index lists), word_token_indices,
+ref_ca_saved_attns - into the flat integer/float tables the kernel reads.  Every integer here (cell ranges, k_fg, k_bg)
+must equal the reference's bit for bit:
+  scale_proportion            utils/utils.py:57-70   (Python banker's round on origin and size separately)
+  union-of-boxes mask          utils/guidance.py:102-114
+  k = max(1, floor(count*p))   utils/guidance.py:136-137 (float32 product, truncation)
+  normalisers                  utils/guidance.py:146,237,270,284
+"""
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import lib
+
+TERM_DTYPE = np.dtype([("type", "<i4"), ("slot", "<i4"), ("mask", "<i4"), ("k_fg", "<i4"), ("k_bg", "<i4"),
+                       ("w_fg", "<f4"), ("w_bg", "<f4"), ("w_ref", "<f4"), ("ref", "<i4")])
+
+
+class XattnLossC(ctypes.Structure):
+    """b200lmd_xattn_loss (include/b200lmd.h)"""
+    _fields_ = [("img_term_off", ctypes.c_void_p), ("terms", ctypes.c_void_p), ("masks", ctypes.c_void_p),
+                ("refs", ctypes.c_void_p), ("slot_tok", ctypes.c_void_p), ("pcol", ctypes.c_void_p),
+                ("counters", ctypes.c_void_p), ("loss_part", ctypes.c_void_p), ("dp_extra", ctypes.c_void_p),
+                ("ext_ld", ctypes.c_int), ("gscale", ctypes.c_float), ("eps", ctypes.c_float)]
+
+
+def scale_proportion(box, H, W):
+    x_min, y_min = round(box[0] * W), round(box[1] * H)
+    bw, bh = round((box[2] - box[0]) * W), round((box[3] - box[1]) * H)
+    x_max, y_max = x_min + bw, y_min + bh
+    return max(x_min, 0), max(y_min, 0), min(x_max, W), min(y_max, H)
+
+
+def _box_list(obj_boxes):
+    if not isinstance(obj_boxes[0], (list, tuple)):
+        return [obj_boxes]
+    return list(obj_boxes)
+
+
+def box_mask(boxes, side):
+    m = np.zeros((side, side), dtype=np.uint8)
+    for b in boxes:
+        x0, y0, x1, y1 = scale_proportion(b, side, side)
+        m[y0:y1, x0:x1] = 1
+    return m.reshape(-1)
+
+
+def topk_sizes(mask, fg_top_p, bg_top_p):
+    s = np.float32(mask.sum())
+    k_fg = max(1, int(np.float32(s * np.float32(fg_top_p))))
+    k_bg = max(1, int(np.float32(np.float32(mask.size - s) * np.float32(bg_top_p))))
+    return k_fg, k_bg
+
+
+@dataclass
+class SampleLayout:
+    """guidance inputs of ONE image, in the reference's own formats"""
+    bboxes: list                       # [phrase] -> box or [boxes]
+    object_positions: list             # [phrase] -> [token indices]
+    word_token_indices: Optional[list] = None
+    ref_maps: Optional[list] = None    # [phrase][box] -> {key: array [heads, n]} for the CURRENT step (or None)
+
+
+@dataclass
+class LossParams:
+    loss_scale: float = 30.0
+    fg_top_p: float = 0.2
+    bg_top_p: float = 0.2
+    fg_weight: float = 1.0
+    bg_weight: float = 1.0
+    ref_ca_loss_weight: float = 1.0
+    ref_word_token_only: bool = False
+    use_ref: bool = False
+
+
+def assign_slots(samples: Sequence[SampleLayout], params: LossParams):
+    """saved-column slots per image: every token any loss term reads, in ascending order"""
+    max_slots = lib().b200lmd_max_loss_slots()
+    slot_tok = np.full((len(samples), max_slots), -1, dtype=np.int32)
+    slot_of = []
+    for b, s in enumerate(samples):
+        toks = set()
+        for o, pos in enumerate(s.object_positions):
+            toks.update(pos)
+            if params.use_ref and s.ref_maps is not None:
+                toks.add(s.word_token_indices[o] if params.ref_word_token_only else pos[-1])
+        toks = sorted(toks)
+        if len(toks) > max_slots:
+            raise ValueError(f"image {b}: {len(toks)} distinct guidance tokens > {max_slots}")
+        slot_tok[b, :len(toks)] = toks
+        slot_of.append({t: i for i, t in enumerate(toks)})
+    return slot_tok, slot_of
+
+
+def build_key_tables(samples: Sequence[SampleLayout], slot_of, key, n, heads, n_keys, params: LossParams):
+    """tables of one attention key (resolution n): returns numpy (term_off, terms, masks, refs)"""
+    side = int(math.sqrt(n))
+    masks, refs, terms = [], [], []
+    term_off = [0]
+    S = params.loss_scale
+    for b, s in enumerate(samples):
+        n_obj = len(s.bboxes)
+        for o in range(n_obj):
+            boxes = _box_list(s.bboxes[o])
+            m = box_mask(boxes, side)
+            k_fg, k_bg = topk_sizes(m, params.fg_top_p, params.bg_top_p)
+            mid = len(masks)
+            masks.append(m)
+            T_o = len(s.object_positions[o])
+            norm = S / (T_o * n_obj * n_keys)
+            for tok in s.object_positions[o]:
+                terms.append((0, slot_of[b][tok], mid, k_fg, k_bg, norm * params.fg_weight, norm * params.bg_weight,
+                              0.0, 0))
+        if params.use_ref and s.ref_maps is not None and params.ref_ca_loss_weight != 0.0:
+            for o in range(n_obj):
+                boxes = _box_list(s.bboxes[o])
+                toks = [s.word_token_indices[o]] if params.ref_word_token_only else [s.object_positions[o][-1]]
+                w = S * params.ref_ca_loss_weight / (len(boxes) * len(toks)) / (n_obj * n_keys) / heads
+                for bi, box in enumerate(boxes):
+                    mid = len(masks)
+                    masks.append(box_mask([box], side))
+                    rid = len(refs)
+                    refs.append(np.asarray(s.ref_maps[o][bi][key], dtype=np.float32).reshape(heads, n))
+                    for tok in toks:
+                        terms.append((1, slot_of[b][tok], mid, 0, 0, 0.0, 0.0, w, rid))
+        term_off.append(len(terms))
+    terms_np = np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, dtype=TERM_DTYPE)
+    masks_np = np.stack(masks) if masks else np.zeros((1, n), dtype=np.uint8)
+    refs_np = np.stack(refs) if refs else np.zeros((1, heads, n), dtype=np.float32)
+    return np.array(term_off, dtype=np.int32), terms_np, masks_np, refs_np
+
+
+class KeyLoss:
+    """device-resident loss tables + scratch of one attention key"""
+
+    def __init__(self, samples, slot_tok_dev, slot_of, key, n, heads, n_keys, params: LossParams, device, ext_ld=80,
+                 gscale=1.0):
+        B = len(samples)
+        off, terms, masks, refs = build_key_tables(samples, slot_of, key, n, heads, n_keys, params)
+        self.n, self.heads, self.B = n, heads, B
+        self.term_off = torch.from_numpy(off).to(device)
+        self.terms = torch.from_numpy(terms.view(np.uint8).reshape(-1).copy() if len(terms) else
+                                      np.zeros(TERM_DTYPE.itemsize, np.uint8)).to(device)
+        self.masks = torch.from_numpy(masks).to(device)
+        self.refs = torch.from_numpy(refs).to(device)
+        self.slot_tok = slot_tok_dev
+        max_slots = lib().b200lmd_max_loss_slots()
+        self.pcol = torch.zeros(B * heads, max_slots, n, device=device, dtype=torch.float32)
+        self.counters = torch.zeros(B * heads, device=device, dtype=torch.int32)
+        self.loss_part = torch.zeros(B * heads, device=device, dtype=torch.float32)
+        self.dp_extra = torch.zeros(B * heads, n, ext_ld, device=device, dtype=torch.float32)
+        self.c = XattnLossC(self.term_off.data_ptr(), self.terms.data_ptr(), self.masks.data_ptr(),
+                            self.refs.data_ptr(), self.slot_tok.data_ptr(), self.pcol.data_ptr(),
+                            self.counters.data_ptr(), self.loss_part.data_ptr(), self.dp_extra.data_ptr(), ext_ld,
+                            gscale, 1e-5)
+
+    def loss_per_image(self):
+        return self.loss_part.view(self.B, self.heads).sum(dim=1)

@@ -166,3 +166,16 @@ def attention_bwd(q, k, v, dO, qt, kt, dOt, lse2, o_tok, do_tok, B, heads, nq, n
         _i(nk_store), _i(B), _i(heads), _i(nq), _i(nk), _i(q.shape[1]), _i(k.shape[1]), _i(d), _f(scale),
         cur_stream()))
     return dq, dk, dv
+
+
+def xattn_fwd(q, k, vt, B, heads, nq, nk, d, scale, loss=None, want_probs=False, save_tok=None, want_lse=False):
+    """fused cross-attention (+ guidance loss when `loss` is a guidance.KeyLoss)"""
+    out = torch.empty(B * nq, heads * d, device=q.device, dtype=torch.float16)
+    lse = torch.zeros(B * heads, q.shape[1], device=q.device, dtype=torch.float32) if want_lse else None
+    probs = torch.empty(B * heads, nq, nk, device=q.device, dtype=torch.float16) if want_probs else None
+    ptok = torch.zeros(B * heads, nq, device=q.device, dtype=torch.float16) if save_tok is not None else None
+    check(lib().b200lmd_xattn_fwd_f16(ptr(q), ptr(k), ptr(vt), ptr(out), _i(heads * d), ptr(lse), ptr(probs),
+                                      ptr(save_tok), ptr(ptok), ctypes.byref(loss.c) if loss is not None else None,
+                                      _i(B), _i(heads), _i(nq), _i(nk), _i(q.shape[1]), _i(k.shape[1]), _i(d),
+                                      _f(scale), cur_stream()))
+    return out, lse, probs, ptok
