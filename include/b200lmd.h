@@ -92,6 +92,10 @@ int b200lmd_cfg_ddim_blend(void* z, const void* eps, int ld_eps, int B, int Cz, 
                            const void* mask, void* stream);
 int b200lmd_latent_update(void* z, const void* grad, int ld_g, int B, int Cz, int HW, float step_scale,
                           float inv_gscale, const int* active, void* stream);
+/* GLIGEN PositionNet front end (models/unet_2d_condition.py:63-114): Fourier box features + phrase embeddings blended
+ * with the learned null features by the object mask -> fp16 [rows, Demb+64] (input of PositionNet.linears[0]). */
+int b200lmd_position_embed(const void* boxes, const void* masks, const void* emb, const void* null_pos,
+                           const void* null_xyxy, void* out_f16, int rows, int Demb, void* stream);
 int b200lmd_attn_delta_slab(const void* dO_slab, const void* o_tok, int ld_o, void* delta, int B, int heads, int nq,
                             int q_alloc, int head_dim, void* stream);
 

@@ -160,3 +160,37 @@ extern "C" int b200lmd_attn_delta_slab(const void* dO_slab, const void* o_tok, i
       (const __half*)dO_slab, b200::round_dp(head_dim), (const __half*)o_tok, ld_o, (float*)delta, B, heads, nq, q_alloc,
       head_dim)));
 }
+
+namespace b200 {
+// GLIGEN PositionNet front end (models/unet_2d_condition.py:63-114): Fourier features of the boxes (8 frequencies,
+// temperature 100, layout [freq][sin|cos][xyxy]) and phrase embeddings, each blended with its learned null feature by
+// the per-object mask; output fp16 [B*N, Demb + 64] = the input of PositionNet.linears[0].
+__global__ void position_embed_kernel(const float* __restrict__ boxes, const float* __restrict__ masks,
+                                      const float* __restrict__ emb, const float* __restrict__ null_pos,
+                                      const float* __restrict__ null_xyxy, __half* __restrict__ out, int rows, int Demb) {
+  const int ld = Demb + 64;
+  const long long total = (long long)rows * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld), c = (int)(i % ld);
+    const float m = masks[r];
+    float v;
+    if (c < Demb) {
+      v = emb[(long long)r * Demb + c] * m + (1.f - m) * null_pos[c];
+    } else {
+      const int k = c - Demb;
+      const int f = k >> 3, sc = (k >> 2) & 1, coord = k & 3;
+      const float a = boxes[r * 4 + coord] * powf(100.f, (float)f / 8.f);
+      v = (sc ? cosf(a) : sinf(a)) * m + (1.f - m) * null_xyxy[k];
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+}  // namespace b200
+
+extern "C" int b200lmd_position_embed(const void* boxes, const void* masks, const void* emb, const void* null_pos,
+                                      const void* null_xyxy, void* out_f16, int rows, int Demb, void* stream) {
+  B200_EW((position_embed_kernel<<<ew_grid((long long)rows * (Demb + 64)), 256, 0, st>>>(
+      (const float*)boxes, (const float*)masks, (const float*)emb, (const float*)null_pos, (const float*)null_xyxy,
+      (__half*)out_f16, rows, Demb)));
+}

@@ -160,7 +160,8 @@ extern "C" int b200lmd_attention_bwd_f16(const void* q, const void* k, const voi
   return guarded([&] {
     cudaStream_t st = (cudaStream_t)stream;
     const float* dl = nullptr;
-    if (delta) {
+    if (delta && !o_tok) dl = (const float*)delta;  // precomputed by the caller (b200lmd_attn_delta_slab)
+    if (delta && o_tok) {
       run_attn_delta((const __half*)do_tok, ld_do, (const __half*)o_tok, ld_o, (float*)delta, B, heads, nq, q_alloc,
                      head_dim, st);
       dl = (const float*)delta;

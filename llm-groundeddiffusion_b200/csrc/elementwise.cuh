@@ -477,7 +477,7 @@ __global__ void cfg_ddim_blend_kernel(float* __restrict__ z, const float* __rest
     }
     float r = sa_p * x0 + sb_p * e;
     if (frozen) {
-      const float mk = mask[p];
+      const float mk = mask[(long long)b * HW + p];   // per-image mask [B, HW]
       r = frozen[i] * mk + r * (1.f - mk);
     }
     z[i] = r;

@@ -1,0 +1,130 @@
+"""What the layout-grounded denoising path needs from its surroundings, as one small interface.
+
+The reference reaches these through module globals (`models.model_dict`: tokenizer, text_encoder, vae, sam_model -
+generation/lmd_plus.py:12-19).  They are NOT part of the B200 hot path (CLIP, VAE and SAM are
+third-party models marked out of scope / "next"), so the path takes them as callables:
+
+  encode_prompts(prompts, negative_prompt)      -> (uncond [1,T,ctx], cond [len(prompts),T,ctx])   models/models.py:63-89
+  phrase_embeddings(phrases)                    -> [len(phrases), 768]  (CLIP pooler_output)        models/pipelines.py:303-304
+  phrase_indices(prompt, phrases, words, add_suffix) -> (object_positions, word_token_indices, prompt)
+                                                                                                   utils/guidance.py:32-89
+  decode(latents [B,4,H,W])                     -> uint8 [B, 8H, 8W, 3] or None                    models/pipelines.py:117-127
+  refine_mask(image, box, H, W)                 -> bool [H, W]                                     models/sam.py:174-213
+
+`SyntheticEnv` is the offline stand-in used by tests and bench.py (no CLIP vocabulary, SD weights or SAM weights exist
+in this environment): seeded embeddings, a whitespace tokenizer, the box raster as "SAM" mask, no VAE.
+`ReferenceEnv` adapts a reference-style model_dict (real tokenizer / text_encoder / vae / sam) to the same interface.
+"""
+import hashlib
+
+import numpy as np
+import torch
+
+from .latents import box_to_mask
+
+
+def _seed_of(s):
+    return int.from_bytes(hashlib.sha256(s.encode()).digest()[:4], "little")
+
+
+class SyntheticEnv:
+    def __init__(self, ctx_dim=768, T=77, latent_hw=(64, 64)):
+        self.ctx_dim, self.T = ctx_dim, T
+        self.latent_hw = latent_hw
+
+    # --- tokenisation: <bos> word word ... <eos>, one token per whitespace-separated word
+    def tokens(self, prompt):
+        return ["<bos>"] + prompt.replace(",", " ,").split() + ["<eos>"]
+
+    def phrase_indices(self, prompt, phrases, words=None, add_suffix=True):
+        """same contract as utils/guidance.py:32-89 (suffixing with "| phrase" when absent, last token of the word)"""
+        for ph in phrases:
+            if ph not in prompt:
+                prompt += "| " + ph
+        toks = self.tokens(prompt)
+        positions, word_idx = [], []
+        for i, ph in enumerate(phrases):
+            pt = self.tokens(ph)[1:-1]
+            start = next(s for s in range(len(toks)) if toks[s:s + len(pt)] == pt)
+            positions.append(list(range(start, start + len(pt))))
+            if words is not None:
+                wt = self.tokens(words[i])[-2]
+                word_idx.append(start + pt.index(wt))
+            else:
+                word_idx.append(positions[0][-1])
+        return positions, word_idx, prompt
+
+    def _embed(self, text, rows):
+        g = torch.Generator().manual_seed(_seed_of(text))
+        return torch.randn(rows, self.ctx_dim, generator=g)
+
+    def encode_prompts(self, prompts, negative_prompt=""):
+        uncond = self._embed("neg:" + negative_prompt, self.T)[None]
+        cond = torch.stack([self._embed("pos:" + p, self.T) for p in prompts])
+        return uncond, cond
+
+    def phrase_embeddings(self, phrases):
+        return torch.stack([self._embed("phrase:" + p, 1)[0] for p in phrases])
+
+    def decode(self, latents):
+        return None
+
+    def refine_mask(self, image, box, H, W):
+        return box_to_mask(box, H, W).bool()
+
+
+class ReferenceEnv:
+    """adapter over the reference's model_dict (tokenizer, text_encoder, vae[, sam]) - see INTEGRATION.md"""
+
+    def __init__(self, model_dict, refine_mask=None, device="cuda"):
+        self.md = model_dict
+        self.device = device
+        self._refine = refine_mask
+
+    def _token_map(self, prompt):
+        ids = self.md.tokenizer([prompt], padding="do_not_pad", max_length=77, return_tensors="np")["input_ids"][0]
+        return [self.md.tokenizer._convert_id_to_token(int(i)) for i in ids.tolist()]
+
+    def phrase_indices(self, prompt, phrases, words=None, add_suffix=True):
+        for ph in phrases:
+            if ph not in prompt:
+                prompt += "| " + ph
+        joined = " ".join(self._token_map(prompt))
+        positions, word_idx = [], []
+        for i, ph in enumerate(phrases):
+            pt = self._token_map(ph)[1:-1]
+            first = len(joined[:joined.index(" ".join(pt)) - 1].split(" "))
+            positions.append(list(range(first, first + len(pt))))
+            if words is None:
+                word_idx.append(positions[0][-1])
+            else:
+                word_idx.append(first + pt.index(self._token_map(words[i])[-2]))
+        return positions, word_idx, prompt
+
+    @torch.no_grad()
+    def encode_prompts(self, prompts, negative_prompt=""):
+        tok, enc = self.md.tokenizer, self.md.text_encoder
+        ti = tok(prompts, padding="max_length", max_length=tok.model_max_length, truncation=True, return_tensors="pt")
+        ui = tok([negative_prompt], padding="max_length", max_length=ti.input_ids.shape[-1], return_tensors="pt")
+        dev = next(enc.parameters()).device
+        return enc(ui.input_ids.to(dev))[0].float().cpu(), enc(ti.input_ids.to(dev))[0].float().cpu()
+
+    @torch.no_grad()
+    def phrase_embeddings(self, phrases):
+        tok, enc = self.md.tokenizer, self.md.text_encoder
+        dev = next(enc.parameters()).device
+        inp = tok(phrases, padding=True, return_tensors="pt").to(dev)
+        return enc(**inp).pooler_output.float().cpu()
+
+    @torch.no_grad()
+    def decode(self, latents):
+        vae = self.md.vae
+        p = next(vae.parameters())
+        img = vae.decode((latents / 0.18215).to(p.device, p.dtype)).sample
+        img = (img / 2 + 0.5).clamp(0, 1).float().cpu().permute(0, 2, 3, 1).numpy()
+        return (img * 255).round().astype("uint8")
+
+    def refine_mask(self, image, box, H, W):
+        if self._refine is not None and image is not None:
+            return torch.as_tensor(self._refine(image, box)).bool()
+        return box_to_mask(box, H, W).bool()

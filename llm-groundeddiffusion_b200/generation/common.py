@@ -1,0 +1,243 @@
+"""Shared machinery of the generation.* plug-ins: spec conversion, the two-phase layout-grounded generation (per-box
+generation -> mask -> latent composition -> overall generation) of generation/lmd.py:215-551 and
+generation/lmd_plus.py:193-520, batched over B independent (prompt, layout) pairs.
+
+The B200 UNet, text/VAE/SAM environment are module state set by the driver before use (the reference binds
+`models.model_dict` at import, generation/lmd_plus.py:12-19):
+    import lgd_b200.generation.common as common
+    common.configure(unet=B200UNet(...), env=ReferenceEnv(model_dict))   # or SyntheticEnv()
+"""
+import numpy as np
+import torch
+
+from .. import latents as L
+from .. import pipelines as P
+from ..guidance import SampleLayout
+
+DEFAULT_SO_NEGATIVE_PROMPT = ("artifacts, blurry, smooth texture, bad quality, distortions, unrealistic, distorted image, "
+                              "bad proportions, duplicate, two, many, group, occlusion, occluded, side, border, collate")
+DEFAULT_OVERALL_NEGATIVE_PROMPT = ("artifacts, blurry, smooth texture, bad quality, distortions, unrealistic, "
+                                   "distorted image, bad proportions, duplicate")
+
+_state = {"unet": None, "env": None}
+
+
+class Output(dict):
+    """EasyDict-style result (attribute + key access), generate.py reads `.image`"""
+    __getattr__ = dict.get
+
+
+def configure(unet, env):
+    _state["unet"], _state["env"] = unet, env
+
+
+def _need():
+    if _state["unet"] is None or _state["env"] is None:
+        raise RuntimeError("lgd_b200.generation: call generation.common.configure(unet=..., env=...) first")
+    return _state["unet"], _state["env"]
+
+
+_NUM = ["zero", "one", "two", "three", "four", "five", "six", "seven", "eight", "nine", "ten", "eleven", "twelve"]
+
+
+def _plural(noun):
+    try:
+        import inflect
+        return inflect.engine().plural_noun(noun)
+    except Exception:
+        if noun.endswith(("s", "x", "z", "ch", "sh")):
+            return noun + "es"
+        if noun.endswith("y") and noun[-2:-1] not in "aeiou":
+            return noun[:-1] + "ies"
+        return noun + "s"
+
+
+def convert_spec(spec, height=512, width=512):
+    """utils/parse.py:313-367: boxes sorted by name, xywh(512-space) -> normalised xyxy, per-box prompts
+    "<bg> with <name>", repeated objects merged into "<count> <plural>" phrases with several boxes."""
+    boxes = sorted(spec["gen_boxes"], key=lambda gb: gb[0])
+    conv = []
+    for name, b in boxes:
+        x0, y0 = b[0] / width, b[1] / height
+        conv.append((name, (x0, y0, x0 + b[2] / width, y0 + b[3] / height)))
+    bg = spec["bg_prompt"]
+    so = [((f"{bg} with {n}" if bg else n), n, n.split(" ")[-1], box) for n, box in conv]
+    names = [n for n, _ in conv]
+    uniq = sorted(set(names))
+    overall = []
+    for n in uniq:
+        bxs = [box for nn, box in conv if nn == n]
+        if len(bxs) > 1:
+            ph = _plural(n.replace("an ", "").replace("a ", ""))
+            ph = (_NUM[len(bxs)] if len(bxs) < len(_NUM) else str(len(bxs))) + " " + ph
+        else:
+            ph = n
+        overall.append((ph, ph.split(" ")[-1], bxs))
+    objs = ", ".join(p for p, _, _ in overall)
+    prompt = (f"{bg} with {objs}" if bg else objs) if objs else bg
+    return so, prompt, overall
+
+
+def centered_box(box, horizontal_only=True, vertical_placement="centered", floor_padding=None):
+    """utils/utils.py:19-44 get_centered_box"""
+    x0, y0, x1, y1 = box
+    w = x1 - x0
+    nx0, nx1 = 0.5 - w / 2, 0.5 + w / 2
+    if horizontal_only:
+        return [nx0, y0, nx1, y1]
+    h = y1 - y0
+    if vertical_placement == "centered":
+        return [nx0, 0.5 - h / 2, nx1, 0.5 + h / 2]
+    ny1 = 1 - floor_padding
+    return [nx0, ny1 - h, nx1, ny1]
+
+
+def _gligen_inputs(env, boxes_per_sample, phrases_per_sample, ctx=768, max_objs=30):
+    """models/pipelines.py:285-321 prepare_gligen_condition (conditional half; the CFG duplication happens in denoise)"""
+    B = len(boxes_per_sample)
+    boxes = torch.zeros(B, max_objs, 4)
+    emb = torch.zeros(B, max_objs, ctx)
+    masks = torch.zeros(B, max_objs)
+    for b, (bx, ph) in enumerate(zip(boxes_per_sample, phrases_per_sample)):
+        n = min(len(bx), max_objs)
+        if n:
+            boxes[b, :n] = torch.tensor(bx[:n], dtype=torch.float32)
+            emb[b, :n] = env.phrase_embeddings(list(ph[:n]))
+            masks[b, :n] = 1
+    return dict(boxes=boxes, positive_embeddings=emb, masks=masks)
+
+
+def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidance, overall_guidance, num_inference_steps,
+                      frozen_step_ratio, so_beta, overall_beta, so_center_box, so_horizontal_center_only,
+                      so_vertical_placement, so_floor_padding, fg_blending_ratio, align_with_overall_bboxes,
+                      horizontal_shift_only, use_ref_ca, ref_ca_loss_weight, so_negative_prompt, overall_negative_prompt,
+                      guidance_scale=7.5, height=512, width=512, keys=None, overall_prompt_overrides=None,
+                      return_latents=False):
+    """Two-phase generation for a batch of specs.  so_guidance / overall_guidance: dict(loss_scale, loss_threshold,
+    max_iter, max_index_step, fg_top_p, bg_top_p, fg_weight, bg_weight) or None."""
+    net, env = _need()
+    keys = list(keys or P.DEFAULT_GUIDANCE_ATTN_KEYS)
+    H, W = height // 8, width // 8
+    steps = num_inference_steps
+    frozen_steps = int(steps * min(max(frozen_step_ratio, 0.0), 1.0))
+    B = len(specs)
+    conv = [convert_spec(s, height, width) for s in specs]
+    so_lists, overall_prompts, overall_pwb = [c[0] for c in conv], [c[1] for c in conv], [c[2] for c in conv]
+    for b in range(B):
+        if overall_prompt_overrides and overall_prompt_overrides[b] and overall_prompt_overrides[b].strip():
+            overall_prompts[b] = overall_prompt_overrides[b].strip()
+        if so_center_box:
+            so_lists[b] = [(p, ph, w, centered_box(bx, so_horizontal_center_only, so_vertical_placement,
+                                                   so_floor_padding)) for p, ph, w, bx in so_lists[b]]
+    so_neg = [((s["extra_neg_prompt"] + ", ") if s.get("extra_neg_prompt") else "") + so_negative_prompt for s in specs]
+    ov_neg = [((s["extra_neg_prompt"] + ", ") if s.get("extra_neg_prompt") else "") + overall_negative_prompt
+              for s in specs]
+
+    # ------------------------------------------------------------------ Phase A: every box of every image, one batch
+    owner, z_list, unc_list, cond_list, lay_list, tok_list, so_boxes, so_phrases = [], [], [], [], [], [], [], []
+    bg_latents = []
+    for b in range(B):
+        boxes = [it[3] for it in so_lists[b]]
+        inp, bg = L.input_latents_for_boxes(bg_seeds[b], fg_seed_starts[b], boxes, fg_blending_ratio, H, W,
+                                            net.cfg.in_channels)
+        bg_latents.append(bg)
+        if not so_lists[b]:
+            continue
+        unc, cnd = env.encode_prompts([it[0] for it in so_lists[b]], so_neg[b])
+        for i, (prompt, phrase, word, box) in enumerate(so_lists[b]):
+            pos, widx, _ = env.phrase_indices(prompt, [phrase], [word], add_suffix=False)
+            owner.append(b)
+            z_list.append(inp[i])
+            unc_list.append(unc)
+            cond_list.append(cnd[i:i + 1])
+            lay_list.append(SampleLayout([list(box)], pos, widx))
+            tok_list.append(widx[0])
+            so_boxes.append(box)
+            so_phrases.append(phrase)
+    latents_all_so, masks_so, saved_so, so_imgs = [], [], [], []
+    if owner and (use_ref_ca or frozen_steps > 0):
+        gspec = None
+        if so_guidance is not None and so_guidance["max_index_step"] > 0:
+            gspec = P.GuidanceSpec(layouts=lay_list, keys=keys, **so_guidance)
+        gl = _gligen_inputs(env, [[b] for b in so_boxes], [[p] for p in so_phrases]) if use_gligen else None
+        resA = P.denoise(net, torch.cat(z_list, 0), torch.cat(unc_list, 0), torch.cat(cond_list, 0), steps,
+                         guidance_scale=guidance_scale, guidance=gspec, gligen=gl, gligen_beta=so_beta,
+                         save_keys=[("down", 2, 1, 0)] + (keys if use_ref_ca else []), save_tok=tok_list,
+                         save_latents=True)
+        imgs = env.decode(resA["latents"])
+        la = resA["latents_all"].cpu()                         # [steps+1, BA, C, H, W]
+        for i in range(len(owner)):
+            img = imgs[i] if imgs is not None else None
+            so_imgs.append(img)
+            masks_so.append(env.refine_mask(img, so_boxes[i], H, W))
+            latents_all_so.append(la[:, i:i + 1])
+            saved_so.append([{k: st[k][i] for k in st} for st in resA["saved"]])     # per step {key: [heads, n]}
+
+    # ------------------------------------------------------------------ composition (host bookkeeping)
+    composed, frozen_masks, ref_maps, layouts, uncs, conds, glb, glp = [], [], [], [], [], [], [], []
+    for b in range(B):
+        idx = [i for i, o in enumerate(owner) if o == b] if latents_all_so else []
+        lat_b = [latents_all_so[i] for i in idx]
+        msk_b = [masks_so[i] for i in idx]
+        phrases = [p for p, _, _ in overall_pwb[b]]
+        words = [w for _, w, _ in overall_pwb[b]]
+        bboxes = [bx for _, _, bx in overall_pwb[b]]
+        flat = [bx for group in bboxes for bx in group]
+        offsets = [(0.0, 0.0)] * len(idx)
+        if align_with_overall_bboxes and lat_b:
+            lat_b, msk_b, offsets = L.align_to_boxes(lat_b, msk_b, flat, horizontal_only=horizontal_shift_only)
+        comp, fg_idx = L.compose(lat_b, msk_b, bg_latents[b], steps)
+        composed.append(comp)
+        frozen_masks.append((fg_idx != 0).float())
+        pos, widx, prompt = env.phrase_indices(overall_prompts[b], phrases, words, add_suffix=True)
+        unc, cnd = env.encode_prompts([prompt], ov_neg[b])
+        uncs.append(unc)
+        conds.append(cnd)
+        layouts.append(SampleLayout([list(map(tuple, g)) for g in bboxes], pos, widx))
+        refs_b = None
+        if use_ref_ca and idx:
+            refs_b, fi = [], 0
+            for group in bboxes:
+                per_phrase = []
+                for _ in group:
+                    steps_maps = saved_so[idx[fi]]
+                    if align_with_overall_bboxes:
+                        dx, dy = offsets[fi]
+                        shifted = []
+                        for st in steps_maps:
+                            d = {}
+                            for k in keys:
+                                m = st[k]
+                                side = int(round(m.shape[1] ** 0.5))
+                                d[k] = L.shift(m.view(m.shape[0], side, side), dx, 0.0 if horizontal_shift_only else dy)\
+                                    .reshape(m.shape[0], -1)
+                            shifted.append(d)
+                        steps_maps = shifted
+                    per_phrase.append(steps_maps)
+                    fi += 1
+                refs_b.append(per_phrase)
+        ref_maps.append(refs_b)
+        glb.append(flat)
+        glp.append([p for p, _, g in overall_pwb[b] for _ in g])
+
+    # ------------------------------------------------------------------ Phase B: overall generation, B images
+    gspec = None
+    if overall_guidance is not None:
+        have_refs = use_ref_ca and any(r is not None for r in ref_maps)
+        gspec = P.GuidanceSpec(layouts=layouts, keys=keys, ref_ca_loss_weight=ref_ca_loss_weight,
+                               ref_word_token_only=True, ref_maps=ref_maps if have_refs else None, **overall_guidance)
+    gl = _gligen_inputs(env, glb, glp) if use_gligen else None
+    comp_all = torch.cat(composed, dim=1)                      # [steps+1, B, C, H, W]
+    resB = P.denoise(net, comp_all[0], torch.cat(uncs, 0), torch.cat(conds, 0), steps, guidance_scale=guidance_scale,
+                     guidance=gspec, frozen_mask=torch.stack(frozen_masks, 0), frozen_latents=comp_all,
+                     frozen_steps=frozen_steps, gligen=gl, gligen_beta=overall_beta)
+    images = env.decode(resB["latents"])
+    outs = []
+    for b in range(B):
+        idx = [i for i, o in enumerate(owner) if o == b] if so_imgs else []
+        o = Output(image=images[b] if images is not None else None, so_img_list=[so_imgs[i] for i in idx])
+        if return_latents:
+            o["latents"] = resB["latents"][b:b + 1]
+            o["guidance_state"] = resB["state"]
+        outs.append(o)
+    return outs

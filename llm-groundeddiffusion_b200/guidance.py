@@ -127,14 +127,13 @@ def build_key_tables(samples: Sequence[SampleLayout], slot_of, key, n, heads, n_
                     mid = len(masks)
                     masks.append(box_mask([box], side))
                     rid = len(refs)
-                    refs.append(np.asarray(s.ref_maps[o][bi][key], dtype=np.float32).reshape(heads, n))
+                    refs.append(s.ref_maps[o][bi][key])
                     for tok in toks:
                         terms.append((1, slot_of[b][tok], mid, 0, 0, 0.0, 0.0, w, rid))
         term_off.append(len(terms))
     terms_np = np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, dtype=TERM_DTYPE)
     masks_np = np.stack(masks) if masks else np.zeros((1, n), dtype=np.uint8)
-    refs_np = np.stack(refs) if refs else np.zeros((1, heads, n), dtype=np.float32)
-    return np.array(term_off, dtype=np.int32), terms_np, masks_np, refs_np
+    return np.array(term_off, dtype=np.int32), terms_np, masks_np, refs
 
 
 class KeyLoss:
@@ -149,7 +148,12 @@ class KeyLoss:
         self.terms = torch.from_numpy(terms.view(np.uint8).reshape(-1).copy() if len(terms) else
                                       np.zeros(TERM_DTYPE.itemsize, np.uint8)).to(device)
         self.masks = torch.from_numpy(masks).to(device)
-        self.refs = torch.from_numpy(refs).to(device)
+        if refs:   # ref maps may be host arrays or device tensors (Phase-A maps stay on the GPU)
+            self.refs = torch.stack([r.to(device, torch.float32) if torch.is_tensor(r) else
+                                     torch.from_numpy(np.asarray(r, dtype=np.float32)).to(device)
+                                     for r in refs]).reshape(len(refs), heads, n).contiguous()
+        else:
+            self.refs = torch.zeros(1, heads, n, device=device, dtype=torch.float32)
         self.slot_tok = slot_tok_dev
         max_slots = lib().b200lmd_max_loss_slots()
         self.pcol = torch.zeros(B * heads, max_slots, n, device=device, dtype=torch.float32)

@@ -1,0 +1,208 @@
+"""Host mirror of the reference's denoising loops (models/pipelines.py) over the B200 UNet.
+
+One batched, timestep-synchronous `denoise` covers generate_semantic_guidance (:129-247), generate_gligen (:324-473) and
+generate_partial_frozen (:541-599); `latent_backward_guidance` (:16-82) becomes a per-image-predicated loop around
+B200UNet.guidance_gradient (no autograd).  The reference is batch-1 (utils/guidance.py:264 squeezes the batch); here B
+independent (prompt, layout) pairs advance together and every data-dependent decision of the reference is kept PER
+IMAGE:
+  * stale-loss loop entry and permanent stop below threshold            pipelines.py:30,161,375,552
+  * max_iter list indexed by step, last element reused                  pipelines.py:21-25
+  * step scale sqrt(1 - alpha_bar_t) (DDIM has no sigmas)               pipelines.py:60-69
+  * CFG batch order [uncond; cond]; guidance pass is cond-only          pipelines.py:44,420; models/models.py:85
+  * GLIGEN: fuser on for index < int(beta*steps); the guidance pass sees the zeroed grounding-mask half
+                                                                        pipelines.py:317,382-384,408-414
+  * frozen blend with latents_all_input[index+1]                        pipelines.py:445-446
+The only host<->device traffic inside a step is the per-image loss read-back that the reference also performs
+(loss.item(), pipelines.py:30).
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import guidance as G
+from ._lib import check, cur_stream, lib, ptr
+
+_i, _f = ctypes.c_int, ctypes.c_float
+
+DEFAULT_GUIDANCE_ATTN_KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+
+
+class DDIMSchedule:
+    """diffusers 0.18 DDIMScheduler arithmetic (scaled_linear 0.00085..0.012, 1000 steps, steps_offset 1,
+    set_alpha_to_one False, eta 0) - host scalars only; the update itself runs in cfg_ddim_blend_kernel."""
+
+    def __init__(self, prediction_type="epsilon"):
+        betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=np.float32) ** 2
+        self.alphas_cumprod = np.cumprod((1.0 - betas).astype(np.float32), dtype=np.float32)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.prediction_type = prediction_type
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = None
+
+    def set_timesteps(self, n):
+        self.num_inference_steps = n
+        self.timesteps = (np.arange(0, n) * (1000 // n)).round()[::-1].astype(np.int64) + 1
+
+    def coefs(self, t):
+        prev_t = int(t) - 1000 // self.num_inference_steps
+        a_t = float(self.alphas_cumprod[int(t)])
+        a_p = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else float(self.final_alpha_cumprod)
+        return a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5
+
+
+@dataclass
+class GuidanceSpec:
+    """semantic_guidance_kwargs of the reference for a batch of images (generation/lmd_plus.py:477-497)"""
+    layouts: List[G.SampleLayout]              # per image: bboxes / object_positions / word tokens
+    keys: list = field(default_factory=lambda: list(DEFAULT_GUIDANCE_ATTN_KEYS))
+    loss_scale: float = 30.0
+    loss_threshold: float = 0.2
+    max_iter: object = 5
+    max_index_step: int = 10
+    fg_top_p: float = 0.2
+    bg_top_p: float = 0.2
+    fg_weight: float = 1.0
+    bg_weight: float = 1.0
+    ref_ca_loss_weight: float = 1.0
+    ref_word_token_only: bool = False
+    # ref_maps[b][phrase][box][step] -> {key: array/tensor [heads, n]} or None
+    ref_maps: Optional[list] = None
+
+
+class GuidanceState:
+    """loss carried across steps per image (the reference's `loss` variable, initialised to 10000.)"""
+
+    def __init__(self, B):
+        self.loss = np.full(B, 10000.0, dtype=np.float64)
+        self.trace = []          # (index, iteration, [loss per image], [active per image])
+        self.iters = []
+
+
+def _heads_of(net, key):
+    cfg = net.cfg
+    if key[0] == "mid":
+        return cfg.heads[-1]
+    if key[0] == "down":
+        return cfg.heads[key[1]]
+    return list(reversed(cfg.heads))[key[1]]
+
+
+def _tokens_of(net, key, H, W):
+    cfg = net.cfg
+    nb = len(cfg.block_out_channels)
+    level = {"down": key[1], "mid": nb - 1, "up": nb - 1 - key[1]}[key[0]]
+    return (H >> level) * (W >> level)
+
+
+def build_losses(net, spec: GuidanceSpec, index, H, W, dev):
+    """device loss tables of every guidance key for step `index`"""
+    B = len(spec.layouts)
+    use_ref = spec.ref_maps is not None
+    layouts = []
+    for b, lay in enumerate(spec.layouts):
+        refs = None
+        if use_ref and spec.ref_maps[b] is not None:
+            refs = [[box[index] for box in phrase] for phrase in spec.ref_maps[b]]
+        layouts.append(G.SampleLayout(lay.bboxes, lay.object_positions, lay.word_token_indices, refs))
+    params = G.LossParams(spec.loss_scale, spec.fg_top_p, spec.bg_top_p, spec.fg_weight, spec.bg_weight,
+                          spec.ref_ca_loss_weight, spec.ref_word_token_only, use_ref)
+    slot_tok, slot_of = G.assign_slots(layouts, params)
+    slot_dev = torch.from_numpy(slot_tok).to(dev)
+    return {k: G.KeyLoss(layouts, slot_dev, slot_of, k, _tokens_of(net, k, H, W), _heads_of(net, k), len(spec.keys),
+                         params, dev, gscale=net.gscale) for k in spec.keys}
+
+
+def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spec: GuidanceSpec, state: GuidanceState,
+                             objs=None, fuser_on=False):
+    """models/pipelines.py:16-82, batched with per-image predicates.  z: device fp32 [B,4,H,W], updated in place."""
+    B, Cz, H, W = z.shape
+    it = np.zeros(B, dtype=np.int64)
+    if index >= spec.max_index_step or all(len(l.bboxes) == 0 for l in spec.layouts):
+        state.iters.append(it.tolist())
+        return
+    mi = spec.max_iter
+    if isinstance(mi, list):
+        mi = mi[index] if len(mi) > index else mi[-1]
+    has_boxes = np.array([len(l.bboxes) > 0 for l in spec.layouts])
+    active = has_boxes & (state.loss / spec.loss_scale > spec.loss_threshold) & (it < mi)
+    losses = None
+    t_dev = torch.full((B,), float(t), device=z.device, dtype=torch.float32)
+    step_scale = float((1.0 - sched.alphas_cumprod[int(t)]) ** 0.5)
+    while active.any():
+        if losses is None:
+            losses = build_losses(net, spec, index, H, W, z.device)
+        grad, loss_new = net.guidance_gradient(z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on)
+        act_dev = torch.from_numpy(active.astype(np.int32)).to(z.device)
+        check(lib().b200lmd_latent_update(ptr(z), ptr(grad), _i(grad.shape[2]), _i(B), _i(Cz), _i(H * W),
+                                          _f(step_scale), _f(1.0 / net.gscale), ptr(act_dev), cur_stream()))
+        state.loss[active] = loss_new[active]
+        it[active] += 1
+        state.trace.append((index, int(it.max()), state.loss.copy().tolist(), active.tolist()))
+        active = active & (state.loss / spec.loss_scale > spec.loss_threshold) & (it < mi)
+    state.iters.append(it.tolist())
+
+
+def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional[GuidanceSpec] = None,
+            frozen_mask=None, frozen_latents=None, frozen_steps=0, gligen=None, gligen_beta=0.3, save_keys=None,
+            save_tok: Optional[Sequence[int]] = None, save_latents=False, prediction_type="epsilon"):
+    """B images in lock-step.  z0 [B,4,H,W] fp32 (any device); uncond [1 or B,T,ctx]; cond [B,T,ctx];
+    frozen_mask [B,H,W] or [H,W] (1 = take the frozen latent), frozen_latents [steps+1,B,4,H,W];
+    gligen: dict(boxes [B,30,4], masks [B,30], positive_embeddings [B,30,768]) of the conditional half;
+    save_keys/save_tok: per step keep the cond-half map column tok[b] of those keys (return_cond_ca_only +
+    return_token_ca_only).  Returns dict(latents, latents_all, saved, state)."""
+    dev = net.dev
+    z = z0.to(dev, torch.float32).contiguous().clone()
+    B, Cz, H, W = z.shape
+    sched = DDIMSchedule(prediction_type)
+    sched.set_timesteps(steps)
+    if uncond.shape[0] == 1:
+        uncond = uncond.expand(B, -1, -1)
+    text = torch.cat([uncond, cond], dim=0)
+    kv = net.set_text(text)
+    heads_of = lambda p: kv.slabs[p][0].shape[0] // (2 * B)
+    kv_cond = lambda p: tuple(s[B * heads_of(p):] for s in kv.slabs[p])
+    objs_main = objs_guid = None
+    n_ground = int(gligen_beta * steps)
+    if gligen is not None:
+        rep2 = lambda x: torch.cat([x, x], dim=0)
+        masks2 = rep2(gligen["masks"]).clone()
+        masks2[:B] = 0                                   # pipelines.py:317 (unconditional half sees null tokens)
+        objs_main = net.position_net(rep2(gligen["boxes"]), masks2, rep2(gligen["positive_embeddings"]))
+        n_obj = objs_main.shape[0] // (2 * B)
+        objs_guid = objs_main[:B * n_obj]                # pipelines.py:382-384: the zeroed-mask half
+    fm = fl = None
+    if frozen_mask is not None:
+        fm = frozen_mask.to(dev, torch.float32).clamp(0.0, 1.0)
+        fm = fm.reshape(1, H * W).expand(B, -1).contiguous() if fm.ndim == 2 else fm.reshape(B, H * W).contiguous()
+        fl = frozen_latents.to(dev, torch.float32).contiguous()
+    tok_dev = None
+    if save_tok is not None:
+        tok_dev = torch.tensor([-1] * B + list(save_tok), dtype=torch.int32, device=dev)
+    state = GuidanceState(B)
+    latents_all = [z.clone()] if save_latents else None
+    saved_all = []
+    for index, t in enumerate(sched.timesteps):
+        fuser_on = gligen is not None and index < n_ground
+        if guidance is not None:
+            latent_backward_guidance(net, sched, z, t, index, kv_cond, guidance, state, objs=objs_guid,
+                                     fuser_on=fuser_on)
+        t2 = torch.full((2 * B,), float(t), device=dev, dtype=torch.float32)
+        eps, saved = net.forward(z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys,
+                                 save_tok=tok_dev)
+        if save_keys is not None:
+            saved_all.append({k: v["tok"][B:] for k, v in saved.items()})
+        sa_t, sb_t, sa_p, sb_p = sched.coefs(t)
+        use_frozen = fm is not None and index < frozen_steps
+        check(lib().b200lmd_cfg_ddim_blend(ptr(z), ptr(eps), _i(eps.shape[3]), _i(B), _i(Cz), _i(H * W),
+                                           _f(guidance_scale), _f(sa_t), _f(sb_t), _f(sa_p), _f(sb_p),
+                                           _i(int(prediction_type == "v_prediction")),
+                                           ptr(fl[index + 1]) if use_frozen else None, ptr(fm) if use_frozen else None,
+                                           cur_stream()))
+        if save_latents:
+            latents_all.append(z.clone())
+    return dict(latents=z, latents_all=torch.stack(latents_all, 0) if save_latents else None, saved=saved_all,
+                state=state)

@@ -1,0 +1,91 @@
+"""GPU parity of the B200 UNet host mirror against the CPU fp32 oracle (oracle/unet_ref.py, pinned to the reference):
+full forward (eps + saved attention maps) and the guidance gradient d loss / d latent from the hand-written backward
+chain vs torch autograd through the oracle.  fp16 storage / fp32 accumulation vs fp32: tolerances stated per check."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _setup(gligen, B, side, seed=0):
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import unet_ref
+    ocfg = unet_ref.UNetConfig.tiny(gligen=gligen)
+    w = unet_ref.make_weights(ocfg, seed=seed)
+    net = B200UNet(UNetConfig.tiny(gligen=gligen), w, "cuda:0")
+    g = torch.Generator().manual_seed(seed + 1)
+    z = torch.randn(B, 4, side, side, generator=g)
+    uncond = torch.randn(1, 77, 768, generator=g).expand(B, -1, -1).contiguous()
+    cond = torch.randn(B, 77, 768, generator=g)
+    return ocfg, w, net, z, uncond, cond
+
+
+def test_forward_matches_oracle(cuda):
+    from oracle import unet_ref
+    B, side = 2, 32
+    ocfg, w, net, z, uncond, cond = _setup(False, B, side)
+    text = torch.cat([uncond, cond], 0)
+    kv = net.set_text(text)
+    t = torch.full((2 * B,), 481.0, device=cuda)
+    eps, saved = net.forward(z.to(cuda), t, kv, rep=2, save_keys=None, save_probs=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_saved = {}
+        ref = unet_ref.unet_forward(w, ocfg, torch.cat([z, z], 0), 481, text, saved=ref_saved)
+    got = eps.permute(0, 3, 1, 2).cpu()
+    r = _rel(got, ref)
+    print("eps rel-L2", r)
+    assert r < 2e-2, r           # fp16 activations through ~60 layers vs fp32
+    assert len(saved) == 16
+    for k in ref_saved:
+        assert (saved[k]["probs"].float().cpu() - ref_saved[k]).abs().max() < 6e-2, k
+
+
+@pytest.mark.parametrize("with_ref", [False, True])
+def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref):
+    from lgd_b200 import guidance as G
+    from oracle import guidance_ref, unet_ref
+    B, side = 2, 32
+    ocfg, w, net, z, uncond, cond = _setup(False, B, side, seed=3)
+    kv = net.set_text(torch.cat([uncond, cond], 0))
+    heads = 8
+    g = torch.Generator().manual_seed(11)
+    layouts = []
+    for b in range(B):
+        bboxes = [[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9), (0.0, 0.0, 0.3, 0.3)]]
+        pos = [[2, 3], [6 + b]]
+        words = [3, 6 + b]
+        refs = None
+        if with_ref:
+            refs = [[{k: torch.softmax(3 * torch.randn(heads, 16 if k[0] == "mid" else 64, generator=g), dim=1).numpy()
+                      for k in KEYS} for _ in boxes] for boxes in bboxes]
+        layouts.append(G.SampleLayout(bboxes, pos, words, refs))
+    params = G.LossParams(loss_scale=5.0, fg_weight=1.0, bg_weight=4.0, ref_ca_loss_weight=2.0,
+                          ref_word_token_only=True, use_ref=with_ref)
+    slot_tok, slot_of = G.assign_slots(layouts, params)
+    slot_dev = torch.from_numpy(slot_tok).to(cuda)
+    losses = {k: G.KeyLoss(layouts, slot_dev, slot_of, k, 16 if k[0] == "mid" else 64, heads, len(KEYS), params, cuda,
+                           gscale=net.gscale) for k in KEYS}
+    t = torch.full((B,), 621.0, device=cuda)
+    kv_cond = lambda p: tuple(s[B * heads:] for s in kv.slabs[p])
+    grad, loss = net.guidance_gradient(z.to(cuda), t, kv_cond, losses)
+    torch.cuda.synchronize()
+    grad = (grad.view(B, side, side, 8)[..., :4].permute(0, 3, 1, 2) / net.gscale).cpu()
+    for b in range(B):
+        zz = z[b:b + 1].clone().requires_grad_(True)
+        saved = {}
+        unet_ref.unet_forward(w, ocfg, zz, 621, cond[b:b + 1], saved=saved, save_keys=KEYS)
+        refs = None
+        if with_ref:
+            refs = [[{k: torch.from_numpy(m[k]) for k in KEYS} for m in obj] for obj in layouts[b].ref_maps]
+        L = guidance_ref.ca_loss({k: v[0] for k, v in saved.items()}, layouts[b].bboxes, layouts[b].object_positions,
+                                 KEYS, 0.2, 0.2, 1.0, 4.0, refs, layouts[b].word_token_indices, 2.0, True) * 5.0
+        gref = torch.autograd.grad(L, [zz])[0]
+        assert abs(float(loss[b]) - float(L)) < 2e-2 * abs(float(L)), (float(loss[b]), float(L))
+        r = _rel(grad[b:b + 1], gref)
+        assert r < 8e-2, r
