@@ -1,0 +1,281 @@
+"""bench.py - images/sec of LMD+ (SD1.4/1.5 + GLIGEN shapes, fp16 activations / fp32 accumulate, 512x512, 50 steps,
+4 boxes per prompt, 8 prompts per GPU) through lgd_b200.generation.lmd_plus.run_batch, plus the tensor-pipe roofline
+of the cross-attention+loss op and the reference's CPU path timed on the host cores.
+
+One "step" = one full batch of 8 images (Phase A: 32 per-box generations x 50 CFG steps with GLIGEN fusers for the first
+40 %; composition; Phase B: 8 overall generations x 50 CFG steps + attention-guidance forward/backward iterations for
+index < 30 + reference-attention transfer).  Synthetic data: seeded random weights with the real layer shapes, seeded
+text embeddings, seeded layouts (no checkpoints, vocabularies or datasets exist offline).  VAE / CLIP / SAM are outside
+the measured path (out of scope / "next"); the SAM mask is the box raster.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "LMD+ SD1.5(+GLIGEN shapes) 512x512, 50 steps, 4 boxes/prompt, 8 prompts/GPU"
+NAMES = ["a red ball", "a blue cube", "a green vase", "a yellow lamp", "a wooden chair", "a black cat", "a white dog",
+         "a purple flower", "a silver car", "an orange bird"]
+
+
+def make_specs(batch, boxes, seed):
+    rng = random.Random(seed)
+    specs = []
+    for _ in range(batch):
+        names = rng.sample(NAMES, boxes)
+        gb = []
+        for n in names:
+            w, h = rng.uniform(0.2, 0.5), rng.uniform(0.2, 0.5)
+            x, y = rng.uniform(0, 1 - w), rng.uniform(0, 1 - h)
+            gb.append((n, [int(x * 512), int(y * 512), int(w * 512), int(h * 512)]))
+        specs.append(dict(prompt="", gen_boxes=gb, bg_prompt="a realistic photo of a living room", extra_neg_prompt=""))
+    return specs
+
+
+class Clocks(threading.Thread):
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops"], d["hbm_gbs"], "measured"
+    return 1590.0, 6650.0, "fallback"
+
+
+def xattn_roofline(dev):
+    """cross-attention+loss op at the config's guidance shape (B=8, n=256, C=1280, heads 8, T=77): algorithmic FLOPs
+    2nC^2 (to_q) + 2nTC (QK^T) + 2nTC (PV) + 2nC^2 (to_out) per sample, timed with CUDA events
+    over the launches that make up the op this round: q projection GEMM, fused attention+loss kernel, to_out GEMM."""
+    from lgd_b200 import guidance as G, ops
+    B, heads, d, n, T, ctx = 8, 8, 160, 256, 77, 768
+    C = heads * d
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(B * n, C, generator=g).half().to(dev)
+    text = torch.randn(B * T, ctx, generator=g).half().to(dev)
+    wq = (torch.randn(C, C, generator=g) * 3 / C ** 0.5).half().to(dev)
+    wkv = (torch.randn(2 * C, ctx, generator=g) * 2 / ctx ** 0.5).half().to(dev)
+    wo = (torch.randn(C, C, generator=g) / C ** 0.5).half().to(dev)
+    bo = torch.zeros(C, device=dev)
+    dp, d16 = ops.round_dp(d), ops.round_d16(d)
+    z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float16)
+    q = z(B * heads, n, dp)
+    k, v, kt, vt = z(B * heads, 80, dp), z(B * heads, 80, dp), z(B * heads, d16, 80), z(B * heads, d16, 80)
+    ops.project_heads2(text, wkv, T, heads, d, 1, rm=(None, k, v), tr=(None, kt, vt))
+    rng = random.Random(0)
+    lay = []
+    for b in range(B):
+        bx, pos = [], []
+        for o in range(4):
+            w_, h_ = rng.uniform(0.2, 0.5), rng.uniform(0.2, 0.5)
+            x0, y0 = rng.uniform(0, 1 - w_), rng.uniform(0, 1 - h_)
+            bx.append([(x0, y0, x0 + w_, y0 + h_)])
+            pos.append([2 * o + 1, 2 * o + 2])
+        lay.append(G.SampleLayout(bx, pos, [p[-1] for p in pos]))
+    params = G.LossParams(loss_scale=5.0, fg_weight=1.0, bg_weight=4.0)
+    st, so = G.assign_slots(lay, params)
+    kl = G.KeyLoss(lay, torch.from_numpy(st).to(dev), so, ("up", 1, 0, 0), n, heads, 4, params, dev, gscale=256.0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    res = x.clone()
+
+    def op():
+        ops.project_heads2(x, wq, n, heads, d, 0, rm=(q, None, None))
+        out, _, _, _ = ops.xattn_fwd(q, k, vt, B, heads, n, T, d, d ** -0.5, loss=kl)
+        return ops.linear(out, wo, bo, res)
+
+    for _ in range(3):
+        op()
+    torch.cuda.synchronize()
+    reps, tot = 20, 0.0
+    for _ in range(reps):
+        flush.zero_()                       # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        op()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / reps
+    flops = B * (2 * n * C * C * 2 + 2 * n * T * C * 2)
+    peak, _, how = peaks()
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+            "traffic": None, "kernel": "cross-attention+loss op (q-proj GEMM + xattn_fwd_kernel + to_out GEMM)",
+            "launches_per_op": 3, "ms_per_op": round(ms, 4), "peak_source": how + " (burst, kernel timed alone)",
+            "shape": {"B": B, "n": n, "C": C, "heads": heads, "T": T}}
+
+
+def cpu_baseline(sample_forwards=1):
+    """the reference's CPU path (oracle restatement of its UNet/loss in fp32 PyTorch, pinned to the unmodified reference
+    in the build container) on this box's host cores: one conditional UNet forward at SD1.5+GLIGEN shapes, batch 1,
+    extrapolated to one LMD+ image = N*50*2 + 50*2 forward-equivalents + 65 guidance iterations (~2.5 forward-equivalents
+    each: truncated forward + backward)."""
+    from oracle import unet_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = unet_ref.UNetConfig.sd15(gligen=True)
+    w = unet_ref.make_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(1, 77, 768, generator=g)
+    gl = dict(boxes=torch.rand(1, 30, 4, generator=g), masks=torch.zeros(1, 30), positive_embeddings=torch.randn(1, 30, 768, generator=g))
+    with torch.no_grad():
+        unet_ref.unet_forward(w, cfg, z, 500, ctx, gligen=gl)          # warm-up
+        t0 = time.time()
+        for _ in range(sample_forwards):
+            unet_ref.unet_forward(w, cfg, z, 500, ctx, gligen=gl)
+        dt = (time.time() - t0) / sample_forwards
+    fwd_equiv = 4 * 50 * 2 + 50 * 2 + 65 * 2.5
+    return {"value": 1.0 / (dt * fwd_equiv), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_forwards} batch-1 fp32 UNet forward(s) at SD1.5+GLIGEN shapes ({dt:.2f} s each), "
+                      f"extrapolated x{fwd_equiv:.0f} forward-equivalents per LMD+ image"}, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--boxes", type=int, default=4)
+    ap.add_argument("--denoise-steps", type=int, default=50)
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": WORKLOAD, "batch_per_gpu": args.batch, "boxes_per_prompt": args.boxes,
+              "denoise_steps": args.denoise_steps, "guidance": "reference semantics (data-dependent iteration counts)",
+              "l2": "inputs exceed L2 (per-step activations >> 126 MB)", "parallelism": f"dp{world}",
+              "outside_path": "CLIP/VAE/SAM (SAM mask = box raster)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, dt = cpu_baseline(sample_forwards=max(1, args.steps))
+        line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": base["value"], "unit": "images/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "impl": "reference", "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import lgd_b200
+    from lgd_b200 import _lib, weights as Wt
+    from lgd_b200.env import SyntheticEnv
+    from lgd_b200.generation import common, lmd_plus
+    from lgd_b200.unet import B200UNet, UNetConfig
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = UNetConfig.sd15(gligen=True)
+    w = Wt.synthetic_weights(cfg, seed=0, device=dev) if rank == 0 else \
+        {n: torch.empty(s, device=dev) for n, s in Wt.parameter_shapes(cfg)}
+    if world > 1:                       # the only collective on the path: start-up broadcast of the frozen weights
+        for n in sorted(w):
+            dist.broadcast(w[n], src=0)
+    net = B200UNet(cfg, w, dev)
+    del w
+    specs = make_specs(args.batch, args.boxes, seed=1000 + rank)
+    seeds = [rank * 1000 + i for i in range(args.batch)]
+    fgs = [s + 123456789 for s in seeds]
+    io = {"h2d": 0, "d2h": 0}
+
+    def step(env):
+        common.configure(net, env)
+        outs = lmd_plus.run_batch(specs, seeds, fgs, num_inference_steps=args.denoise_steps, return_latents=True)
+        lat = torch.cat([o["latents"] for o in outs], 0)
+        host = lat.cpu()                                  # device -> host read of the step's result
+        io["d2h"] = host.numel() * host.element_size()
+        return host
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(env, k):
+        barrier()
+        clk = Clocks(local)
+        clk.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step(env)
+        e1.record()
+        barrier()
+        clk.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.launch_count() - n0, clk.summary()
+
+    env_res = SyntheticEnv(cache_device=dev)       # inputs resident in HBM (memoised on device)
+    env_host = SyntheticEnv(cache_device=None)     # inputs produced on the host each call (pinned), copied inside
+    for _ in range(args.warmup):
+        step(env_res)
+    ms, launches, clocks = timed(env_res, args.steps)
+    ms_e2e, _, _ = timed(env_host, args.steps)
+    io["h2d"] = env_host.bytes_out // max(1, args.steps * 1) if hasattr(env_host, "bytes_out") else 0
+    imgs = args.batch * world * args.steps
+    line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": imgs / (ms * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": config, "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": io["h2d"],
+                    "d2h_bytes_per_step": io["d2h"]}}
+    if rank == 0:
+        if not args.no_roofline:
+            line["roofline"] = xattn_roofline(dev)
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(1)[0]
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,9 +27,20 @@ def lib():
     return _lib
 
 
+_calls = 0
+
+
 def check(rc):
+    """every C-ABI op call funnels through here; each successful call launched >= 1 of our kernels"""
+    global _calls
     if rc != 0:
         raise B200Error(lib().b200lmd_last_error().decode())
+    _calls += 1
+
+
+def launch_count():
+    """lower bound on the number of our kernel launches so far (C-ABI op calls; several launch 2-4 kernels)"""
+    return _calls
 
 
 def ptr(t):

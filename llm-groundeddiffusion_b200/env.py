@@ -28,9 +28,14 @@ def _seed_of(s):
 
 
 class SyntheticEnv:
-    def __init__(self, ctx_dim=768, T=77, latent_hw=(64, 64)):
+    def __init__(self, ctx_dim=768, T=77, latent_hw=(64, 64), cache_device=None):
         self.ctx_dim, self.T = ctx_dim, T
         self.latent_hw = latent_hw
+        # cache_device set: embeddings are memoised ON the device (inputs resident in HBM);
+        # unset: every call produces pinned host tensors that the path copies host->device itself.
+        self.cache_device = cache_device
+        self._cache = {}
+        self.bytes_out = 0
 
     # --- tokenisation: <bos> word word ... <eos>, one token per whitespace-separated word
     def tokens(self, prompt):
@@ -55,8 +60,19 @@ class SyntheticEnv:
         return positions, word_idx, prompt
 
     def _embed(self, text, rows):
+        key = (text, rows)
+        if self.cache_device is not None and key in self._cache:
+            return self._cache[key]
         g = torch.Generator().manual_seed(_seed_of(text))
-        return torch.randn(rows, self.ctx_dim, generator=g)
+        t = torch.randn(rows, self.ctx_dim, generator=g)
+        if self.cache_device is not None:
+            t = t.to(self.cache_device)
+            self._cache[key] = t
+        else:
+            if torch.cuda.is_available():
+                t = t.pin_memory()
+            self.bytes_out += t.numel() * t.element_size()
+        return t
 
     def encode_prompts(self, prompts, negative_prompt=""):
         uncond = self._embed("neg:" + negative_prompt, self.T)[None]

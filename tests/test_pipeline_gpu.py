@@ -1,0 +1,94 @@
+"""GPU parity of the batched denoising loops (llm-groundeddiffusion_b200/pipelines.py) against the oracle loops
+(oracle/pipeline_ref.py, pinned to the reference's models/pipelines.py): iteration counts must match exactly (integer
+artefacts), loss traces and final latents within the fp16-vs-fp32 tolerance stated per check."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _common(gligen, B=2, side=32, seed=0):
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import unet_ref
+    ocfg = unet_ref.UNetConfig.tiny(gligen=gligen)
+    w = unet_ref.make_weights(ocfg, seed=seed)
+    net = B200UNet(UNetConfig.tiny(gligen=gligen), w, "cuda:0")
+    g = torch.Generator().manual_seed(seed + 5)
+    z0 = torch.randn(B, 4, side, side, generator=g)
+    uncond = torch.randn(1, 77, 768, generator=g)
+    cond = torch.randn(B, 77, 768, generator=g)
+    return ocfg, w, net, g, z0, uncond, cond
+
+
+def test_semantic_guidance_loop(cuda):
+    from lgd_b200 import guidance as G, pipelines as P
+    from oracle import pipeline_ref
+    B, steps = 2, 4
+    ocfg, w, net, g, z0, uncond, cond = _common(False, B)
+    lay = [G.SampleLayout([[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9)]], [[2, 3], [6]], [3, 6]),
+           G.SampleLayout([[(0.3, 0.1, 0.9, 0.5), (0.0, 0.6, 0.4, 1.0)]], [[4]], [4])]
+    spec = P.GuidanceSpec(layouts=lay, keys=KEYS, loss_scale=30, loss_threshold=0.2, max_iter=[2, 1, 1],
+                          max_index_step=3, fg_weight=1.0, bg_weight=4.0)
+    res = P.denoise(net, z0, uncond, cond, steps, guidance=spec, save_keys=[("down", 2, 1, 0)] + KEYS,
+                    save_tok=[3, 4], save_latents=True)
+    torch.cuda.synchronize()
+    iters = list(zip(*res["state"].iters))     # per image
+    for b in range(B):
+        og = pipeline_ref.GuidanceCfg(lay[b].bboxes, lay[b].object_positions, KEYS, 30, 0.2, [2, 1, 1], 3, 0.2, 0.2,
+                                      1.0, 4.0)
+        tr = []
+        ref = pipeline_ref.denoise(w, ocfg, z0[b:b + 1], uncond, cond[b:b + 1], steps, g=og,
+                                   save_keys=[("down", 2, 1, 0)] + KEYS, save_token=[3, 4][b], trace=tr)
+        assert list(iters[b]) == ref["iters"], (iters[b], ref["iters"])
+        r = _rel(res["latents"][b:b + 1].cpu(), ref["latents"])
+        print("image", b, "final-latent rel-L2", r, "oracle loss", ref["loss"], "ours", res["state"].loss[b])
+        assert r < 5e-2, r
+        assert abs(res["state"].loss[b] - ref["loss"]) < 3e-2 * abs(ref["loss"])
+        for s_ref, s in zip(ref["saved"], res["saved"]):
+            for k in s_ref:
+                assert (s_ref[k][0, :, :, 0] - s[k][b].float().cpu()).abs().max() < 6e-2
+
+
+def test_gligen_ref_frozen_loop(cuda):
+    from lgd_b200 import guidance as G, pipelines as P
+    from oracle import pipeline_ref
+    B, steps, side = 2, 4, 32
+    ocfg, w, net, g, z0, uncond, cond = _common(True, B)
+    frozen = torch.randn(steps + 1, B, 4, side, side, generator=g)
+    frozen[0] = z0
+    fmask = (torch.rand(B, side, side, generator=g) > 0.5).float()
+    boxes = [[(0.1, 0.2, 0.6, 0.7), (0.5, 0.4, 0.95, 0.9)], [(0.2, 0.2, 0.8, 0.8)]]
+    lay = [G.SampleLayout([[boxes[0][0]], [boxes[0][1]]], [[2, 3], [6]], [3, 6]),
+           G.SampleLayout([[boxes[1][0]]], [[5, 6]], [6])]
+    heads = 8
+    refs = [[[[{k: torch.softmax(3 * torch.randn(heads, 16 if k[0] == "mid" else 64, generator=g), dim=1)
+                for k in KEYS} for _ in range(steps)] for _ in phrase] for phrase in l.bboxes] for l in lay]
+    gl = dict(boxes=torch.zeros(B, 30, 4), masks=torch.zeros(B, 30), positive_embeddings=torch.zeros(B, 30, 768))
+    for b in range(B):
+        n = len(boxes[b])
+        gl["boxes"][b, :n] = torch.tensor(boxes[b])
+        gl["masks"][b, :n] = 1
+        gl["positive_embeddings"][b, :n] = torch.randn(n, 768, generator=g)
+    spec = P.GuidanceSpec(layouts=lay, keys=KEYS, loss_scale=5, loss_threshold=0.01, max_iter=[2, 1],
+                          max_index_step=3, fg_weight=1.0, bg_weight=4.0, ref_ca_loss_weight=2.0,
+                          ref_word_token_only=True, ref_maps=refs)
+    res = P.denoise(net, z0, uncond, cond, steps, guidance=spec, frozen_mask=fmask, frozen_latents=frozen,
+                    frozen_steps=2, gligen=gl, gligen_beta=0.5)
+    torch.cuda.synchronize()
+    iters = list(zip(*res["state"].iters))
+    for b in range(B):
+        og = pipeline_ref.GuidanceCfg(lay[b].bboxes, lay[b].object_positions, KEYS, 5, 0.01, [2, 1], 3, 0.2, 0.2, 1.0,
+                                      4.0, refs[b], lay[b].word_token_indices, 2.0, True)
+        ref = pipeline_ref.denoise(w, ocfg, z0[b:b + 1], uncond, cond[b:b + 1], steps, g=og, frozen_mask=fmask[b],
+                                   frozen_latents=frozen[:, b:b + 1], frozen_steps=2,
+                                   gligen={k: v[b:b + 1] for k, v in gl.items()}, gligen_beta=0.5)
+        assert list(iters[b]) == ref["iters"], (iters[b], ref["iters"])
+        r = _rel(res["latents"][b:b + 1].cpu(), ref["latents"])
+        print("image", b, "final-latent rel-L2", r, "oracle loss", ref["loss"], "ours", res["state"].loss[b])
+        assert r < 5e-2, r
+        assert abs(res["state"].loss[b] - ref["loss"]) < 3e-2 * abs(ref["loss"])
