@@ -205,15 +205,12 @@ def main():
     from lgd_b200.unet import B200UNet, UNetConfig
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    from lgd_b200 import parallel
+    import torch.distributed as dist
+    parallel.init("nccl", dev)
     cfg = UNetConfig.sd15(gligen=True)
-    w = Wt.synthetic_weights(cfg, seed=0, device=dev) if rank == 0 else \
-        {n: torch.empty(s, device=dev) for n, s in Wt.parameter_shapes(cfg)}
-    if world > 1:                       # the only collective on the path: start-up broadcast of the frozen weights
-        for n in sorted(w):
-            dist.broadcast(w[n], src=0)
+    # the only collective on the path: start-up NCCL broadcast of the frozen weights from rank 0
+    w = parallel.broadcast_weights(Wt.parameter_shapes(cfg), lambda: Wt.synthetic_weights(cfg, seed=0, device=dev), dev)
     net = B200UNet(cfg, w, dev)
     del w
     specs = make_specs(args.batch, args.boxes, seed=1000 + rank)
@@ -248,10 +245,7 @@ def main():
         barrier()
         clk.stop_flag = True
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _lib.launch_count() - n0, clk.summary()
+        return parallel.max_over_ranks(ms, dev), _lib.launch_count() - n0, clk.summary()
 
     env_res = SyntheticEnv(cache_device=dev)       # inputs resident in HBM (memoised on device)
     env_host = SyntheticEnv(cache_device=None)     # inputs produced on the host each call (pinned), copied inside

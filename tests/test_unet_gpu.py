@@ -88,4 +88,5 @@ def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref):
         gref = torch.autograd.grad(L, [zz])[0]
         assert abs(float(loss[b]) - float(L)) < 2e-2 * abs(float(L)), (float(loss[b]), float(L))
         r = _rel(grad[b:b + 1], gref)
+        print('image', b, 'loss', float(loss[b]), float(L), 'grad rel-L2', r)
         assert r < 8e-2, r
