@@ -30,6 +30,13 @@ NAMES = ["a red ball", "a blue cube", "a green vase", "a yellow lamp", "a wooden
          "a purple flower", "a silver car", "an orange bird"]
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def make_specs(batch, boxes, seed):
     rng = random.Random(seed)
     specs = []
@@ -147,7 +154,7 @@ def cpu_baseline(sample_forwards=1):
     extrapolated to one LMD+ image = N*50*2 + 50*2 forward-equivalents + 65 guidance iterations (~2.5 forward-equivalents
     each: truncated forward + backward)."""
     from oracle import unet_ref
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)       # beyond ~64 threads the fp32 conv/GEMM kernels stop scaling
     torch.set_num_threads(cores)
     cfg = unet_ref.UNetConfig.sd15(gligen=True)
     w = unet_ref.make_weights(cfg, seed=0)
@@ -177,6 +184,7 @@ def main():
     ap.add_argument("--boxes", type=int, default=4)
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,8 +219,10 @@ def main():
     cfg = UNetConfig.sd15(gligen=True)
     # the only collective on the path: start-up NCCL broadcast of the frozen weights from rank 0
     w = parallel.broadcast_weights(Wt.parameter_shapes(cfg), lambda: Wt.synthetic_weights(cfg, seed=0, device=dev), dev)
+    log("weights ready")
     net = B200UNet(cfg, w, dev)
     del w
+    log("unet prepared")
     specs = make_specs(args.batch, args.boxes, seed=1000 + rank)
     seeds = [rank * 1000 + i for i in range(args.batch)]
     fgs = [s + 123456789 for s in seeds]
@@ -249,10 +259,14 @@ def main():
 
     env_res = SyntheticEnv(cache_device=dev)       # inputs resident in HBM (memoised on device)
     env_host = SyntheticEnv(cache_device=None)     # inputs produced on the host each call (pinned), copied inside
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         step(env_res)
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
     ms, launches, clocks = timed(env_res, args.steps)
+    log(f"timed (resident inputs): {ms:.1f} ms for {args.steps} step(s)")
     ms_e2e, _, _ = timed(env_host, args.steps)
+    log(f"timed (host inputs, e2e): {ms_e2e:.1f} ms")
     io["h2d"] = env_host.bytes_out // max(1, args.steps * 1) if hasattr(env_host, "bytes_out") else 0
     imgs = args.batch * world * args.steps
     line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": imgs / (ms * 1e-3), "unit": "images/s",
@@ -264,8 +278,10 @@ def main():
     if rank == 0:
         if not args.no_roofline:
             line["roofline"] = xattn_roofline(dev)
-        if world == 1:
+            log("roofline micro-benchmark done")
+        if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(1)[0]
+            log("cpu baseline done")
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

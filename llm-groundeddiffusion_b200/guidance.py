@@ -65,7 +65,8 @@ class SampleLayout:
     bboxes: list                       # [phrase] -> box or [boxes]
     object_positions: list             # [phrase] -> [token indices]
     word_token_indices: Optional[list] = None
-    ref_maps: Optional[list] = None    # [phrase][box] -> {key: array [heads, n]} for the CURRENT step (or None)
+    # [phrase][box] -> {key: array/tensor [heads, n]} for the current step, or a LIST of such dicts over steps
+    ref_maps: Optional[list] = None
 
 
 @dataclass
@@ -127,7 +128,7 @@ def build_key_tables(samples: Sequence[SampleLayout], slot_of, key, n, heads, n_
                     mid = len(masks)
                     masks.append(box_mask([box], side))
                     rid = len(refs)
-                    refs.append(s.ref_maps[o][bi][key])
+                    refs.append(s.ref_maps[o][bi])       # resolved per step in KeyLoss.set_step
                     for tok in toks:
                         terms.append((1, slot_of[b][tok], mid, 0, 0, 0.0, 0.0, w, rid))
         term_off.append(len(terms))
@@ -148,12 +149,12 @@ class KeyLoss:
         self.terms = torch.from_numpy(terms.view(np.uint8).reshape(-1).copy() if len(terms) else
                                       np.zeros(TERM_DTYPE.itemsize, np.uint8)).to(device)
         self.masks = torch.from_numpy(masks).to(device)
-        if refs:   # ref maps may be host arrays or device tensors (Phase-A maps stay on the GPU)
-            self.refs = torch.stack([r.to(device, torch.float32) if torch.is_tensor(r) else
-                                     torch.from_numpy(np.asarray(r, dtype=np.float32)).to(device)
-                                     for r in refs]).reshape(len(refs), heads, n).contiguous()
-        else:
-            self.refs = torch.zeros(1, heads, n, device=device, dtype=torch.float32)
+        # reference maps live in ONE static device buffer (pointer baked into captured CUDA graphs); set_step() refills
+        # it in place.  Entries may be host arrays or device tensors (Phase-A maps stay on the GPU).
+        self.key, self.device = key, device
+        self.ref_entries = refs
+        self.refs = torch.zeros(max(1, len(refs)), heads, n, device=device, dtype=torch.float32)
+        self.set_step(0)
         self.slot_tok = slot_tok_dev
         max_slots = lib().b200lmd_max_loss_slots()
         self.pcol = torch.zeros(B * heads, max_slots, n, device=device, dtype=torch.float32)
@@ -164,6 +165,14 @@ class KeyLoss:
                             self.refs.data_ptr(), self.slot_tok.data_ptr(), self.pcol.data_ptr(),
                             self.counters.data_ptr(), self.loss_part.data_ptr(), self.dp_extra.data_ptr(), ext_ld,
                             gscale, 1e-5)
+
+    def set_step(self, index):
+        """load the reference maps of denoising step `index` (utils/guidance.py:181) into the static buffer"""
+        for i, e in enumerate(self.ref_entries):
+            m = (e[index] if isinstance(e, list) else e)[self.key]
+            if not torch.is_tensor(m):
+                m = torch.from_numpy(np.asarray(m, dtype=np.float32))
+            self.refs[i].copy_(m.reshape(self.heads, self.n), non_blocking=True)
 
     def loss_per_image(self):
         return self.loss_part.view(self.B, self.heads).sum(dim=1)

@@ -73,6 +73,22 @@ class GuidanceSpec:
     ref_maps: Optional[list] = None
 
 
+class CudaGraph:
+    """capture a launch-only callable once (after an eager warm-up run) and replay it; all tensors it touches must be
+    static (updated in place between replays)"""
+
+    def __init__(self, fn):
+        fn()                                   # eager warm-up: one-time func attributes, allocator warm-up
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
 class GuidanceState:
     """loss carried across steps per image (the reference's `loss` variable, initialised to 10000.)"""
 
@@ -80,6 +96,9 @@ class GuidanceState:
         self.loss = np.full(B, 10000.0, dtype=np.float64)
         self.trace = []          # (index, iteration, [loss per image], [active per image])
         self.iters = []
+        self.losses = None       # device loss tables, built at the first guided iteration and reused
+        self.graphs = {}         # fuser_on -> CudaGraph of the guidance forward+backward
+        self.t_dev = None
 
 
 def _heads_of(net, key):
@@ -99,25 +118,27 @@ def _tokens_of(net, key, H, W):
 
 
 def build_losses(net, spec: GuidanceSpec, index, H, W, dev):
-    """device loss tables of every guidance key for step `index`"""
+    """device loss tables of every guidance key (built once per loop; KeyLoss.set_step refreshes the per-step
+    reference maps in place)"""
     B = len(spec.layouts)
     use_ref = spec.ref_maps is not None
     layouts = []
     for b, lay in enumerate(spec.layouts):
-        refs = None
-        if use_ref and spec.ref_maps[b] is not None:
-            refs = [[box[index] for box in phrase] for phrase in spec.ref_maps[b]]
+        refs = spec.ref_maps[b] if use_ref else None       # [phrase][box] -> list over steps of {key: [heads, n]}
         layouts.append(G.SampleLayout(lay.bboxes, lay.object_positions, lay.word_token_indices, refs))
     params = G.LossParams(spec.loss_scale, spec.fg_top_p, spec.bg_top_p, spec.fg_weight, spec.bg_weight,
                           spec.ref_ca_loss_weight, spec.ref_word_token_only, use_ref)
     slot_tok, slot_of = G.assign_slots(layouts, params)
     slot_dev = torch.from_numpy(slot_tok).to(dev)
-    return {k: G.KeyLoss(layouts, slot_dev, slot_of, k, _tokens_of(net, k, H, W), _heads_of(net, k), len(spec.keys),
-                         params, dev, gscale=net.gscale) for k in spec.keys}
+    out = {k: G.KeyLoss(layouts, slot_dev, slot_of, k, _tokens_of(net, k, H, W), _heads_of(net, k), len(spec.keys),
+                        params, dev, gscale=net.gscale) for k in spec.keys}
+    for kl in out.values():
+        kl.set_step(index)
+    return out
 
 
 def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spec: GuidanceSpec, state: GuidanceState,
-                             objs=None, fuser_on=False):
+                             objs=None, fuser_on=False, use_graphs=False):
     """models/pipelines.py:16-82, batched with per-image predicates.  z: device fp32 [B,4,H,W], updated in place."""
     B, Cz, H, W = z.shape
     it = np.zeros(B, dtype=np.int64)
@@ -129,13 +150,26 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
         mi = mi[index] if len(mi) > index else mi[-1]
     has_boxes = np.array([len(l.bboxes) > 0 for l in spec.layouts])
     active = has_boxes & (state.loss / spec.loss_scale > spec.loss_threshold) & (it < mi)
-    losses = None
-    t_dev = torch.full((B,), float(t), device=z.device, dtype=torch.float32)
+    losses = state.losses
+    if losses is not None:
+        for kl in losses.values():
+            kl.set_step(index)
+    if state.t_dev is None:
+        state.t_dev = torch.empty(B, device=z.device, dtype=torch.float32)
+    t_dev = state.t_dev
+    t_dev.fill_(float(t))
     step_scale = float((1.0 - sched.alphas_cumprod[int(t)]) ** 0.5)
     while active.any():
         if losses is None:
-            losses = build_losses(net, spec, index, H, W, z.device)
-        grad, loss_new = net.guidance_gradient(z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on)
+            losses = state.losses = build_losses(net, spec, index, H, W, z.device)
+        if use_graphs:
+            if fuser_on not in state.graphs:
+                state.graphs[fuser_on] = CudaGraph(lambda: net.guidance_gradient_launch(
+                    z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on))
+            grad, parts = state.graphs[fuser_on]()
+        else:
+            grad, parts = net.guidance_gradient_launch(z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on)
+        loss_new = net.reduce_loss(parts, B)
         act_dev = torch.from_numpy(active.astype(np.int32)).to(z.device)
         check(lib().b200lmd_latent_update(ptr(z), ptr(grad), _i(grad.shape[2]), _i(B), _i(Cz), _i(H * W),
                                           _f(step_scale), _f(1.0 / net.gscale), ptr(act_dev), cur_stream()))
@@ -148,7 +182,7 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
 
 def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional[GuidanceSpec] = None,
             frozen_mask=None, frozen_latents=None, frozen_steps=0, gligen=None, gligen_beta=0.3, save_keys=None,
-            save_tok: Optional[Sequence[int]] = None, save_latents=False, prediction_type="epsilon"):
+            save_tok: Optional[Sequence[int]] = None, save_latents=False, prediction_type="epsilon", use_graphs=True):
     """B images in lock-step.  z0 [B,4,H,W] fp32 (any device); uncond [1 or B,T,ctx]; cond [B,T,ctx];
     frozen_mask [B,H,W] or [H,W] (1 = take the frozen latent), frozen_latents [steps+1,B,4,H,W];
     gligen: dict(boxes [B,30,4], masks [B,30], positive_embeddings [B,30,768]) of the conditional half;
@@ -183,18 +217,26 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
     if save_tok is not None:
         tok_dev = torch.tensor([-1] * B + list(save_tok), dtype=torch.int32, device=dev)
     state = GuidanceState(B)
+    fwd_graphs = {}
+    t2 = torch.empty(2 * B, device=dev, dtype=torch.float32)
     latents_all = [z.clone()] if save_latents else None
     saved_all = []
     for index, t in enumerate(sched.timesteps):
         fuser_on = gligen is not None and index < n_ground
         if guidance is not None:
             latent_backward_guidance(net, sched, z, t, index, kv_cond, guidance, state, objs=objs_guid,
-                                     fuser_on=fuser_on)
-        t2 = torch.full((2 * B,), float(t), device=dev, dtype=torch.float32)
-        eps, saved = net.forward(z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys,
-                                 save_tok=tok_dev)
-        if save_keys is not None:
-            saved_all.append({k: v["tok"][B:] for k, v in saved.items()})
+                                     fuser_on=fuser_on, use_graphs=use_graphs)
+        t2.fill_(float(t))
+        if use_graphs:
+            if fuser_on not in fwd_graphs:
+                fwd_graphs[fuser_on] = CudaGraph(lambda: net.forward(
+                    z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys, save_tok=tok_dev))
+            eps, saved = fwd_graphs[fuser_on]()
+        else:
+            eps, saved = net.forward(z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys,
+                                     save_tok=tok_dev)
+        if save_keys is not None:       # graph outputs are static buffers: keep a copy of this step's maps
+            saved_all.append({k: v["tok"][B:].clone() for k, v in saved.items()})
         sa_t, sb_t, sa_p, sb_p = sched.coefs(t)
         use_frozen = fm is not None and index < frozen_steps
         check(lib().b200lmd_cfg_ddim_blend(ptr(z), ptr(eps), _i(eps.shape[3]), _i(B), _i(Cz), _i(H * W),

@@ -695,9 +695,10 @@ class B200UNet:
         eps = self._network(z, t, rep, st)
         return eps, saved
 
-    def guidance_gradient(self, z, t, kv_cond, losses: Dict[tuple, "G.KeyLoss"], objs=None, fuser_on=False):
-        """cond-only pass truncated at the last guidance key + hand-written backward.
-        Returns (grad fp32 NHWC-8 [B, HW, 8] = gscale * d(loss*loss_scale)/dz, per-image scaled loss [B])"""
+    def guidance_gradient_launch(self, z, t, kv_cond, losses: Dict[tuple, "G.KeyLoss"], objs=None, fuser_on=False):
+        """launch-only part (CUDA-graph capturable: no host synchronisation): cond-only pass truncated at the last
+        guidance key + hand-written backward.  Returns (grad fp32 NHWC-8 [B, HW, 8] = gscale * d(loss*loss_scale)/dz,
+        loss partials [n_keys, B*heads] on the device)"""
         self.tape, self.grads, self._keep = [], {}, []
         self.latent_grad = None
         order = [k for _, k in self._key_order() if k in losses]
@@ -711,13 +712,20 @@ class B200UNet:
         tape, self.tape = self.tape, None
         for fn in reversed(tape):
             fn()
-        # per-image scaled loss: fixed-order host sum of the per-(key, image, head) partials the kernels wrote
-        parts = torch.stack([losses[k].loss_part for k in order]).cpu().numpy()
-        B = z.shape[0]
-        loss = parts.reshape(len(order), B, -1).sum(axis=2).sum(axis=0)
+        parts = torch.stack([losses[k].loss_part for k in order])
         g = self.latent_grad
         self.grads, self._keep = {}, []
-        return g, loss
+        return g, parts
+
+    @staticmethod
+    def reduce_loss(parts, B):
+        """per-image scaled loss: fixed-order host sum of the per-(key, image, head) partials the kernels wrote"""
+        p = parts.cpu().numpy()
+        return p.reshape(p.shape[0], B, -1).sum(axis=2).sum(axis=0)
+
+    def guidance_gradient(self, z, t, kv_cond, losses, objs=None, fuser_on=False):
+        g, parts = self.guidance_gradient_launch(z, t, kv_cond, losses, objs=objs, fuser_on=fuser_on)
+        return g, self.reduce_loss(parts, z.shape[0])
 
     def _key_order(self):
         cfg = self.cfg
