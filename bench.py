@@ -129,12 +129,15 @@ def xattn_roofline(dev):
     for _ in range(3):
         op()
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()          # device time only: the three launches replayed back to back
+    with torch.cuda.graph(graph):
+        op()
     reps, tot = 20, 0.0
     for _ in range(reps):
-        flush.zero_()                       # L2 flush between timed iterations
+        flush.zero_()                       # L2 flush (256 MB > 126 MB L2) between timed iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        op()
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
