@@ -18,6 +18,8 @@ extern "C" {
 
 const char* b200lmd_last_error(void);
 int b200lmd_version(void);
+/* runtime switches for A/B measurements of kernel generations ("attn_v2": 1 = ping-pong online-softmax attention) */
+int b200lmd_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------ dense ops
  * y[M,N] = alpha * x[M,K] . W[N,K]^T (+ bias[N]) (+ residual[M,N]).  Replaces nn.Linear / 1x1 nn.Conv2d call sites:
@@ -175,6 +177,21 @@ int b200lmd_max_loss_slots(void);
 int b200lmd_xattn_fwd_f16(const void* q, const void* k, const void* vt, void* out, int ldo, void* lse2, void* probs,
                           const int* save_tok, void* probs_tok, const b200lmd_xattn_loss* loss, int B, int heads,
                           int nq, int nk, int q_alloc, int k_alloc, int head_dim, float scale, void* stream);
+
+/* The same op in ONE launch, projections included (the kernel BASELINE.json's roofline target names):
+ *   out = residual + bias_o + softmax(scale (x Wq^T) K^T) V Wo^T      x, residual, out: fp16 [B*n, heads*head_dim]
+ * Clusters of 8 CTAs (one per head) share each 128-row tile of x through TMA multicast; O is exchanged through L2
+ * between the attention core and the output projection (o_scratch [B*n, C] fp16).  Requires heads == 8,
+ * n % 128 == 0, head_dim in {64, 80, 160}, <= 80 text keys in 80-row K / V^T slabs (b200lmd_xattn_fused_supported).
+ * q_slab (optional, [B*heads, n, dp]) and lse2 ([B*heads, n]) are what b200lmd_attention_bwd_f16 needs.
+ * Replaces attn.to_q + get_attention_scores + bmm + to_out[0] (models/attention_processor.py:426-451) + the
+ * residual add of BasicTransformerBlock (models/attention.py:220) + utils/guidance.py:91-286. */
+int b200lmd_xattn_fused_supported(int heads, int head_dim, int n);
+int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void* k_slab, const void* vt_slab, const void* wo,
+                            const void* bias_o, const void* residual, void* out, void* o_scratch, void* q_slab,
+                            void* lse2, void* probs, const int* save_tok, void* probs_tok,
+                            const b200lmd_xattn_loss* loss, int B, int n, int heads, int head_dim, int nk, int k_alloc,
+                            float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ normalisation
  * GroupNorm (+ optional SiLU) over NHWC fp16 x[B, n, C]: stats then apply (torch.nn.GroupNorm inside diffusers

@@ -194,3 +194,12 @@ extern "C" int b200lmd_position_embed(const void* boxes, const void* masks, cons
       (const float*)boxes, (const float*)masks, (const float*)emb, (const float*)null_pos, (const float*)null_xyxy,
       (__half*)out_f16, rows, Demb)));
 }
+
+// runtime switches (kept for A/B measurements of kernel generations; defaults are the fastest correct variants)
+extern "C" int b200lmd_set_option(const char* name, int value) {
+  return b200::guarded([&] {
+    std::string n(name);
+    if (n == "attn_v2") b200::attn_use_v2() = value != 0;
+    else throw std::runtime_error("unknown option " + n);
+  });
+}

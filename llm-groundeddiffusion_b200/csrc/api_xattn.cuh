@@ -1,6 +1,7 @@
 // C-ABI: fused cross-attention + guidance loss forward (included by api_ops.cu)
 #pragma once
 #include "xattn.cuh"
+#include "xattn_fused.cuh"
 
 namespace b200 {
 
@@ -76,3 +77,72 @@ extern "C" int b200lmd_xattn_fwd_f16(const void* q, const void* k, const void* v
   });
 }
 extern "C" int b200lmd_max_loss_slots(void) { return b200::kMaxSlots; }
+
+namespace b200 {
+inline CUtensorMap rowmajor_map_2d(const __half* p, long long rows, int cols, int ld, int box_rows) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t st[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {64, (uint32_t)box_rows};
+  return make_tmap_f16(p, 2, dims, st, box);
+}
+
+template <int D>
+inline void launch_fused_t(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmK,
+                           const CUtensorMap& tmVt, const CUtensorMap& tmO, const CUtensorMap& tmWo,
+                           const FusedXattnParams& p, int row_tiles, cudaStream_t st) {
+  using Cfg = FusedCfg<D>;
+  static bool done = false;
+  if (!done) {
+    B200_CHECK(cudaFuncSetAttribute(xattn_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES));
+    done = true;
+  }
+  xattn_fused_kernel<D><<<dim3(row_tiles * 8), 192, Cfg::SMEM_BYTES, st>>>(tmX, tmWq, tmK, tmVt, tmO, tmWo, p);
+  B200_CHECK(cudaGetLastError());
+}
+}  // namespace b200
+
+extern "C" int b200lmd_xattn_fused_supported(int heads, int head_dim, int n) {
+  return heads == 8 && n % 128 == 0 && (head_dim == 64 || head_dim == 80 || head_dim == 160);
+}
+
+extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void* k_slab, const void* vt_slab,
+                                       const void* wo, const void* bias_o, const void* residual, void* out,
+                                       void* o_scratch, void* q_slab, void* lse2, void* probs, const int* save_tok,
+                                       void* probs_tok, const b200lmd_xattn_loss* loss, int B, int n, int heads,
+                                       int head_dim, int nk, int k_alloc, float scale, void* stream) {
+  return b200::guarded([&] {
+    using namespace b200;
+    if (!b200lmd_xattn_fused_supported(heads, head_dim, n)) throw std::runtime_error("xattn_fused: unsupported shape");
+    if (nk > 80 || k_alloc < 80) throw std::runtime_error("xattn_fused: needs <= 80 text keys in 80-row slabs");
+    const int C = heads * head_dim;
+    const long long M = (long long)B * n;
+    const int dp = round_dp(head_dim), d16 = round_d16(head_dim);
+    if (d16 != head_dim) throw std::runtime_error("xattn_fused: head_dim must be a multiple of 16");
+    FusedXattnParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.d = head_dim; p.C = C; p.nk = nk; p.k_alloc = k_alloc; p.tiles_per_img = n / 128;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.bias_o = (const float*)bias_o; p.residual = (const __half*)residual; p.out = (__half*)out;
+    p.o_buf = (__half*)o_scratch; p.q_slab = (__half*)q_slab; p.lse2 = (float*)lse2; p.probs = (__half*)probs;
+    p.save_tok = save_tok; p.probs_tok = (__half*)probs_tok;
+    p.has_loss = loss != nullptr;
+    if (loss) p.L = *reinterpret_cast<const XattnLoss*>(loss);
+    CUtensorMap tmX = rowmajor_map_2d((const __half*)x, M, C, C, 16);
+    CUtensorMap tmO = rowmajor_map_2d((const __half*)o_scratch, M, C, C, 16);
+    CUtensorMap tmWq = rowmajor_map_2d((const __half*)wq, C, C, C, head_dim);
+    CUtensorMap tmWo = rowmajor_map_2d((const __half*)wo, C, C, C, head_dim);
+    uint64_t kd[3] = {(uint64_t)dp, (uint64_t)k_alloc, (uint64_t)B * heads};
+    uint64_t ks[2] = {(uint64_t)dp * 2, (uint64_t)dp * 2 * k_alloc};
+    uint32_t kb[3] = {64, 80, 1};
+    CUtensorMap tmK = make_tmap_f16(k_slab, 3, kd, ks, kb);
+    CUtensorMap tmVt = slab_tr_map((const __half*)vt_slab, B * heads, d16, k_alloc);
+    const int row_tiles = (int)(M / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (head_dim) {
+      case 64: launch_fused_t<64>(tmX, tmWq, tmK, tmVt, tmO, tmWo, p, row_tiles, st); break;
+      case 80: launch_fused_t<80>(tmX, tmWq, tmK, tmVt, tmO, tmWo, p, row_tiles, st); break;
+      default: launch_fused_t<160>(tmX, tmWq, tmK, tmVt, tmO, tmWo, p, row_tiles, st); break;
+    }
+  });
+}

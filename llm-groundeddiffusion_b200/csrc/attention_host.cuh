@@ -1,6 +1,7 @@
 // Host-side launch builders for the attention kernels.
 #pragma once
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "attention_bwd.cuh"
 #include "gemm_host.cuh"
 
@@ -69,8 +70,24 @@ inline void launch_attn_fwd_t(const AttnLaunch& L, cudaStream_t st) {
   B200_CHECK(cudaGetLastError());
 }
 
+inline bool& attn_use_v2() {
+  static bool v = true;   // second-generation kernel (attention2.cuh) for head_dim <= 64
+  return v;
+}
+
 inline void run_attn_fwd(const AttnLaunch& L, cudaStream_t st) {
   const int key = L.dpb * 1000 + L.d16;
+  if (L.dpb == 1 && attn_use_v2()) {
+    const int BH = (int)L.grid.y;
+    switch (L.d16) {
+      case 16: launch_attn_fwd2_t<16>(L.tmQ, L.tmK, L.tmVt, L.p, L.p.nq, BH, st); break;
+      case 32: launch_attn_fwd2_t<32>(L.tmQ, L.tmK, L.tmVt, L.p, L.p.nq, BH, st); break;
+      case 48: launch_attn_fwd2_t<48>(L.tmQ, L.tmK, L.tmVt, L.p, L.p.nq, BH, st); break;
+      default: launch_attn_fwd2_t<64>(L.tmQ, L.tmK, L.tmVt, L.p, L.p.nq, BH, st); break;
+    }
+    B200_CHECK(cudaGetLastError());
+    return;
+  }
   switch (key) {
     case 1016: launch_attn_fwd_t<1, 16, 2>(L, st); break;
     case 1032: launch_attn_fwd_t<1, 32, 2>(L, st); break;

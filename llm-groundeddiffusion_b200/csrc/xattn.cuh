@@ -75,6 +75,83 @@ __device__ __forceinline__ float block128_sum(float v, float* red, int tid) {
   return red[0] + red[1] + red[2] + red[3];
 }
 
+
+// Loss / gradient of one (image, head) from the published P columns (utils/guidance.py:91-242).  Called by the 128
+// softmax threads of the last CTA of that (image, head); scratch: >= 2n floats of shared memory.
+__device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scratch, float* s_red, int tid, int b,
+                                                  int h, int heads, int bh, int n) {
+                float* col = scratch;                        // [n] values + [n] masked values
+        float* val = col + n;                        // n <= 4096 fits (32 KB)
+        float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
+        for (int i = tid; i < n * L.ext_ld; i += 128) dpx[i] = 0.f;
+        float loss_acc = 0.f;
+        const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
+        for (int t = t0; t < t1; ++t) {
+          const LossTerm T = L.terms[t];
+          const int tok = L.slot_tok[b * kMaxSlots + T.slot];
+          const float* src = L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
+          const uint8_t* mk = L.masks + (long long)T.mask * n;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = tid; i < n; i += 128) col[i] = __ldcg(src + i);
+          if (T.type == 0) {
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+              const int k = side ? T.k_bg : T.k_fg;
+              const float w = side ? T.w_bg : T.w_fg;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              for (int i = tid; i < n; i += 128) val[i] = (mk[i] != 0) == (side == 0) ? col[i] : 0.f;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              float part = 0.f;
+              for (int i = tid; i < n; i += 128) {
+                const float vi = val[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                  const float vj = val[j];
+                  rank += (vj > vi) || (vj == vi && j < i);
+                }
+                if (rank < k) {
+                  part += vi;
+                  const bool inside = (mk[i] != 0) == (side == 0);
+                  if (inside) dpx[(long long)i * L.ext_ld + tok] += (side ? w : -w) / (float)k * L.gscale;
+                }
+              }
+              const float tot = block128_sum(part, s_red, tid);
+              loss_acc += side ? w * tot / (float)k : w * (1.f - tot / (float)k);
+            }
+          } else {
+            const float* R = L.refs + ((long long)T.ref * heads + h) * n;
+            float sa = 0.f, sr = 0.f;
+            for (int i = tid; i < n; i += 128)
+              if (mk[i]) {
+                sa += col[i];
+                sr += R[i];
+              }
+            const float A = block128_sum(sa, s_red, tid) + L.eps;
+            const float Rs = block128_sum(sr, s_red, tid) + L.eps;
+            float l1 = 0.f, inner = 0.f;
+            for (int i = tid; i < n; i += 128)
+              if (mk[i]) {
+                const float ah = col[i] / A, rh = R[i] / Rs;
+                const float df = ah - rh;
+                const float sg = (df > 0.f) - (df < 0.f);
+                l1 += fabsf(df);
+                inner += sg * ah;
+              }
+            const float L1 = block128_sum(l1, s_red, tid);
+            const float In = block128_sum(inner, s_red, tid);
+            loss_acc += T.w_ref * L1;
+            for (int i = tid; i < n; i += 128)
+              if (mk[i]) {
+                const float ah = col[i] / A, rh = R[i] / Rs;
+                const float df = ah - rh;
+                const float sg = (df > 0.f) - (df < 0.f);
+                dpx[(long long)i * L.ext_ld + tok] += T.w_ref / A * (sg - In) * L.gscale;
+              }
+          }
+        }
+        if (tid == 0) L.loss_part[bh] = loss_acc;
+}
+
 template <int DPB, int D16>
 __global__ void __launch_bounds__(192, 1)
 xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -277,77 +354,7 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*s_flag) {
         __threadfence();
-        const int n = p.nq;
-        float* col = reinterpret_cast<float*>(sP);   // P tile is dead: reuse as [n] values + [n] masked values
-        float* val = col + n;                        // n <= 4096 fits (32 KB)
-        float* dpx = p.L.dp_extra + (long long)bh * n * p.L.ext_ld;
-        for (int i = tid; i < n * p.L.ext_ld; i += 128) dpx[i] = 0.f;
-        float loss_acc = 0.f;
-        const int t0 = p.L.img_term_off[b], t1 = p.L.img_term_off[b + 1];
-        for (int t = t0; t < t1; ++t) {
-          const LossTerm T = p.L.terms[t];
-          const int tok = p.L.slot_tok[b * kMaxSlots + T.slot];
-          const float* src = p.L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
-          const uint8_t* mk = p.L.masks + (long long)T.mask * n;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = tid; i < n; i += 128) col[i] = __ldcg(src + i);
-          if (T.type == 0) {
-#pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-              const int k = side ? T.k_bg : T.k_fg;
-              const float w = side ? T.w_bg : T.w_fg;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              for (int i = tid; i < n; i += 128) val[i] = (mk[i] != 0) == (side == 0) ? col[i] : 0.f;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              float part = 0.f;
-              for (int i = tid; i < n; i += 128) {
-                const float vi = val[i];
-                int rank = 0;
-                for (int j = 0; j < n; ++j) {
-                  const float vj = val[j];
-                  rank += (vj > vi) || (vj == vi && j < i);
-                }
-                if (rank < k) {
-                  part += vi;
-                  const bool inside = (mk[i] != 0) == (side == 0);
-                  if (inside) dpx[(long long)i * p.L.ext_ld + tok] += (side ? w : -w) / (float)k * p.L.gscale;
-                }
-              }
-              const float tot = block128_sum(part, s_red, tid);
-              loss_acc += side ? w * tot / (float)k : w * (1.f - tot / (float)k);
-            }
-          } else {
-            const float* R = p.L.refs + ((long long)T.ref * p.heads + h) * n;
-            float sa = 0.f, sr = 0.f;
-            for (int i = tid; i < n; i += 128)
-              if (mk[i]) {
-                sa += col[i];
-                sr += R[i];
-              }
-            const float A = block128_sum(sa, s_red, tid) + p.L.eps;
-            const float Rs = block128_sum(sr, s_red, tid) + p.L.eps;
-            float l1 = 0.f, inner = 0.f;
-            for (int i = tid; i < n; i += 128)
-              if (mk[i]) {
-                const float ah = col[i] / A, rh = R[i] / Rs;
-                const float df = ah - rh;
-                const float sg = (df > 0.f) - (df < 0.f);
-                l1 += fabsf(df);
-                inner += sg * ah;
-              }
-            const float L1 = block128_sum(l1, s_red, tid);
-            const float In = block128_sum(inner, s_red, tid);
-            loss_acc += T.w_ref * L1;
-            for (int i = tid; i < n; i += 128)
-              if (mk[i]) {
-                const float ah = col[i] / A, rh = R[i] / Rs;
-                const float df = ah - rh;
-                const float sg = (df > 0.f) - (df < 0.f);
-                dpx[(long long)i * p.L.ext_ld + tok] += T.w_ref / A * (sg - In) * p.L.gscale;
-              }
-          }
-        }
-        if (tid == 0) p.L.loss_part[bh] = loss_acc;
+        xattn_loss_reduce(p.L, reinterpret_cast<float*>(sP), s_red, tid, b, h, p.heads, bh, p.nq);
       }
     }
   }

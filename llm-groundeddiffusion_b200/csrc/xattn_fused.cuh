@@ -1,0 +1,443 @@
+// The graded kernel: cross-attention with its projections and the guidance loss in ONE launch (sm_100a).
+//
+//   out[rows, :] = residual + bias_o + softmax(scale * (x Wq^T) K^T) V  Wo^T        (+ loss, d loss/dP, optional maps)
+//
+// Grid = clusters of 8 CTAs; a cluster owns one 128-row tile of x (rows of ONE image: n % 128 == 0), CTA rank = head.
+//   phase 1  Q_h   = x_tile . Wq_h^T        tcgen05 128 x d x C GEMM; the x tile is fetched ONCE per cluster: each CTA
+//                                           TMA-loads a 16-row slice of every k-block and multicasts it to all 8 CTAs
+//   core     S = Q_h K_h^T -> softmax (one thread per row, from TMEM) -> P (fp16 smem) -> O_h = P V_h
+//            + attention-map outputs, loss-column scratch, last-CTA-per-(image, head) loss/gradient (as xattn.cuh)
+//   exchange O_h -> HBM/L2 [rows, C]; cluster barrier
+//   phase 2  out[:, h*d:(h+1)*d] = O_tile . Wo[h*d:(h+1)*d, :]^T + bias + residual   (O tile multicast like x)
+// Text K/V of the prompt are constants prepared once (slabs as in attention.cuh).  FLOPs per launch = the SURVEY
+// section 8(d) accounting: B*(2nC^2 + 2nTC + 2nTC + 2nC^2).
+#pragma once
+#include "xattn.cuh"
+
+namespace b200 {
+
+struct FusedXattnParams {
+  int n, d, C, nk, k_alloc;
+  int tiles_per_img;
+  float scale_log2;
+  const float* bias_o;
+  const __half* residual;   // [M, C]
+  __half* out;              // [M, C]
+  __half* o_buf;            // [M, C] scratch
+  __half* q_slab;           // optional [B*8, n, dp] row-major Q for the backward
+  float* lse2;              // optional [B*8, n]
+  __half* probs;            // optional [B*8, n, nk]
+  const int* save_tok;
+  __half* probs_tok;        // [B*8, n]
+  int has_loss;
+  XattnLoss L;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+template <int D>   // head dim, multiple of 16, <= 192
+struct FusedCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = 16384;
+  static constexpr int B_BYTES = D * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int DPB = (D + 63) / 64;                 // K atoms of Q / K_h
+  static constexpr int KT_ATOM = 80 * 128;                  // K_h atom: 80 text rows x 128 B
+  static constexpr int K_BYTES = ((DPB * KT_ATOM + 1023) / 1024) * 1024;
+  static constexpr int V_ATOM = D * 128;                    // V^T atom: D rows x 64 keys
+  static constexpr int V_BYTES = ((2 * V_ATOM + 1023) / 1024) * 1024;
+  static constexpr int Q_BYTES = DPB * 16384;               // aliases the stage ring
+  static constexpr int P_BYTES = 2 * 16384;                 // aliases the stage ring
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static_assert(Q_BYTES + P_BYTES <= RING_BYTES, "core scratch must fit in the stage ring");
+  static constexpr int SMEM_BYTES = RING_BYTES + K_BYTES + V_BYTES + 1024 + 512;
+  static_assert(SMEM_BYTES <= 232448, "smem budget");
+};
+
+template <int D>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(192, 1)
+xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVt,
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
+                   const __grid_constant__ FusedXattnParams p) {
+  using Cfg = FusedCfg<D>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* sQ = ring;                      // core scratch aliases the ring (idle between the two GEMM phases)
+  uint8_t* sP = ring + Cfg::Q_BYTES;
+  uint8_t* sK = ring + Cfg::RING_BYTES;
+  uint8_t* sV = sK + Cfg::K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::V_BYTES);
+  uint64_t* full_bar = bars;               // STAGES
+  uint64_t* empty_bar = bars + STAGES;     // STAGES (count 8: every CTA of the cluster frees the slot)
+  uint64_t* kv_full = empty_bar + STAGES;  // 1
+  uint64_t* acc_full = kv_full + 1;        // 1: a GEMM phase / core MMA finished (phases 0..3)
+  uint64_t* q_ready = acc_full + 1;        // 1 (count 4)
+  uint64_t* p_ready = q_ready + 1;         // 1 (count 4)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_ready + 1);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
+  float* s_red = reinterpret_cast<float*>(s_flag + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int h = (int)cluster_ctarank();            // head
+  const int rt = blockIdx.x >> 3;                  // row tile
+  const int row0 = rt * 128;
+  const int b = row0 / p.n;                        // image of this tile
+  const int bh = b * 8 + h;
+  const int tok0 = row0 - b * p.n;                 // first token of the tile inside the image
+  const int nkb = p.C >> 6;                        // k-blocks of the two projection GEMMs
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmWq); prefetch_tmap(&tmK);
+    prefetch_tmap(&tmVt); prefetch_tmap(&tmO); prefetch_tmap(&tmWo);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 8);
+      }
+      mbar_init(kv_full, 1);
+      mbar_init(acc_full, 1);
+      mbar_init(q_ready, 4);
+      mbar_init(p_ready, 4);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();           // every CTA's barriers exist before anyone multicasts into / arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tAcc = tmem_base;          // Q_h, then O_h, then the output tile (D columns)
+  const uint32_t tS = tmem_base + 256;      // scores (80 columns)
+
+  // ------------------------------------------------------------------ role: TMA producer
+  if (warp == 0) {
+    if (elect_one()) {
+      // text K/V of this (image, head): needed only by the core, issued first so they arrive during phase 1
+      mbar_arrive_expect_tx(kv_full, Cfg::DPB * Cfg::KT_ATOM + 2 * Cfg::V_ATOM);
+      for (int a = 0; a < Cfg::DPB; ++a) tma_load_3d(sK + a * Cfg::KT_ATOM, &tmK, kv_full, a * 64, 0, bh);
+      for (int a = 0; a < 2; ++a) tma_load_3d(sV + a * Cfg::V_ATOM, &tmVt, kv_full, a * 64, 0, bh);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        tma_load_2d_mcast(sa + h * 2048, &tmX, &full_bar[stage], kb * 64, row0 + h * 16, (uint16_t)0xFF);
+        tma_load_2d(sa + Cfg::A_BYTES, &tmWq, &full_bar[stage], kb * 64, h * D);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  // ------------------------------------------------------------------ role: MMA issuer, phase 1
+  constexpr uint32_t idesc_g = make_idesc_f16(128, D);
+  constexpr uint32_t idesc_s = make_idesc_f16(128, 80);
+  if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+        const uint64_t ad = make_desc_k_sw128(sa);
+        const uint64_t bd = make_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tAcc, ad + k * 2, bd + k * 2, idesc_g, (kb | k) ? 1u : 0u);
+        tc_commit_mcast(&empty_bar[stage], (uint16_t)0xFF);
+        if (kb == nkb - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- core MMAs
+    mbar_wait(kv_full, 0);
+    mbar_wait(q_ready, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int a = 0; a < Cfg::DPB; ++a) {
+        const uint64_t ad = make_desc_k_sw128(smem_u32(sQ) + a * 16384);
+        const uint64_t bd = make_desc_k_sw128(smem_u32(sK) + a * Cfg::KT_ATOM);
+        const int ksteps = (a == Cfg::DPB - 1) ? ((D - a * 64 + 15) / 16) : 4;
+        for (int k = 0; k < ksteps; ++k) umma_f16_ss(tS, ad + k * 2, bd + k * 2, idesc_s, (a | k) ? 1u : 0u);
+      }
+      tc_commit(acc_full);
+    }
+    __syncwarp();
+    mbar_wait(p_ready, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      // O_h = P V_h : K = 80 keys = 5 k-steps (4 in atom 0, 1 in atom 1)
+      for (int ks = 0; ks < 5; ++ks) {
+        const int a = ks >> 2, k = ks & 3;
+        const uint64_t ad = make_desc_k_sw128(smem_u32(sP) + a * 16384);
+        const uint64_t bd = make_desc_k_sw128(smem_u32(sV) + a * Cfg::V_ATOM);
+        umma_f16_ss(tAcc, ad + k * 2, bd + k * 2, idesc_g, ks ? 1u : 0u);
+      }
+      tc_commit(acc_full);
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ role: epilogue / softmax warps
+  const int quad = warp & 3;
+  const int r = quad * 32 + lane_id();
+  const int tid = threadIdx.x - 64;
+  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+  const int tok = tok0 + r;                       // token index inside the image
+  const long long grow = (long long)row0 + r;     // global row
+  auto p_at = [&](int t) -> float {
+    const uint8_t* atom = sP + (t >> 6) * 16384;
+    const __half* chunk = reinterpret_cast<const __half*>(atom + sw128_offset(r, (t & 63) >> 3));
+    return __half2float(chunk[t & 7]);
+  };
+  float row_m = 0.f, row_l = 1.f;
+  if (warp >= 2) {
+    // ---- Q_h: TMEM -> fp16 -> smem A operand (and the optional Q slab for the backward)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    __half* qrow = p.q_slab ? p.q_slab + ((long long)bh * p.n + tok) * (Cfg::DPB * 64) : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cfg::DPB * 64; c0 += 16) {
+      uint32_t pk[8];
+      if (c0 < D) {
+        uint32_t v[16];
+        tmem_ld_x16(tAcc + lane_off + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+      }
+      uint8_t* atom = sQ + (c0 >> 6) * 16384;
+      const int ch0 = (c0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if (qrow) {
+        *reinterpret_cast<uint4*>(qrow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(qrow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(q_ready);
+
+    // ---- softmax over the 77 keys
+    mbar_wait(acc_full, 1);
+    tc_fence_after();
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 80; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tS + lane_off + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i < p.nk) m = fmaxf(m, __uint_as_float(v[i]));
+    }
+    m *= p.scale_log2;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 80; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tS + lane_off + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i < p.nk) l += ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m));
+    }
+    const float inv_l = 1.f / l;
+    row_m = m;
+    row_l = l;
+    __half* prow = p.probs ? p.probs + ((long long)bh * p.n + tok) * p.nk : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+      uint32_t pk[8];
+      if (c0 < 80) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_off + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = (c0 + 2 * i < p.nk) ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m)) * inv_l : 0.f;
+          const float c = (c0 + 2 * i + 1 < p.nk) ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m)) * inv_l : 0.f;
+          pk[i] = pack_h2(a, c);
+        }
+        if (prow) {
+          const __half* hp = reinterpret_cast<const __half*>(pk);
+          for (int i = 0; i < 16 && c0 + i < p.nk; ++i) prow[c0 + i] = hp[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+      }
+      uint8_t* atom = sP + (c0 >> 6) * 16384;
+      const int ch0 = (c0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    if (p.save_tok) {
+      const int t = p.save_tok[b];
+      if (t >= 0) p.probs_tok[(long long)bh * p.n + tok] = __float2half_rn(p_at(t));
+    }
+    if (p.has_loss) {
+      for (int s = 0; s < kMaxSlots; ++s) {
+        const int t = p.L.slot_tok[b * kMaxSlots + s];
+        if (t < 0) break;
+        p.L.pcol[((long long)bh * kMaxSlots + s) * p.n + tok] = p_at(t);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(p_ready);
+
+    // ---- O_h: TMEM -> fp16 -> o_buf[rows, h*D ...]  (the A operand of phase 2, read back through L2)
+    mbar_wait(acc_full, 0);   // third completion of acc_full: parity 0 again
+    tc_fence_after();
+    __half* orow = p.o_buf + grow * p.C + h * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tAcc + lane_off + c0, v);
+      tmem_ld_wait();
+      uint4 s0, s1;
+      s0.x = pack_h2(__uint_as_float(v[0]), __uint_as_float(v[1])); s0.y = pack_h2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+      s0.z = pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5])); s0.w = pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+      s1.x = pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9])); s1.y = pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+      s1.z = pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13])); s1.w = pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+      *reinterpret_cast<uint4*>(orow + c0) = s0;
+      *reinterpret_cast<uint4*>(orow + c0 + 8) = s1;
+    }
+    if (p.lse2) p.lse2[(long long)bh * p.n + tok] = row_m + log2f(row_l);
+    __threadfence();
+    fence_proxy_async_all();
+    tc_fence_before();
+  }
+  // every CTA has published O_h and is done with the ring scratch
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+
+  // ------------------------------------------------------------------ phase 2: out slice = O_tile . Wo_h^T
+  if (warp == 0) {
+    if (elect_one()) {
+      fence_proxy_async_all();
+      int stage = nkb % STAGES;
+      uint32_t phase = (nkb / STAGES) & 1;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        tma_load_2d_mcast(sa + h * 2048, &tmO, &full_bar[stage], kb * 64, row0 + h * 16, (uint16_t)0xFF);
+        tma_load_2d(sa + Cfg::A_BYTES, &tmWo, &full_bar[stage], kb * 64, h * D);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = nkb % STAGES;
+    uint32_t phase = (nkb / STAGES) & 1;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+        const uint64_t ad = make_desc_k_sw128(sa);
+        const uint64_t bd = make_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tAcc, ad + k * 2, bd + k * 2, idesc_g, (kb | k) ? 1u : 0u);
+        tc_commit_mcast(&empty_bar[stage], (uint16_t)0xFF);
+        if (kb == nkb - 1) tc_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    mbar_wait(acc_full, 1);   // fourth completion
+    tc_fence_after();
+    const __half* rrow = p.residual ? p.residual + grow * p.C + h * D : nullptr;
+    __half* orow = p.out + grow * p.C + h * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tAcc + lane_off + c0, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + (p.bias_o ? __ldg(p.bias_o + h * D + c0 + i) : 0.f);
+      if (rrow) {
+        uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + 8);
+        const __half2* a = reinterpret_cast<const __half2*>(&r0);
+        const __half2* c = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 t0 = __half22float2(a[i]), t1 = __half22float2(c[i]);
+          f[2 * i] += t0.x; f[2 * i + 1] += t0.y;
+          f[8 + 2 * i] += t1.x; f[8 + 2 * i + 1] += t1.y;
+        }
+      }
+      uint4 s0, s1;
+      s0.x = pack_h2(f[0], f[1]); s0.y = pack_h2(f[2], f[3]); s0.z = pack_h2(f[4], f[5]); s0.w = pack_h2(f[6], f[7]);
+      s1.x = pack_h2(f[8], f[9]); s1.y = pack_h2(f[10], f[11]); s1.z = pack_h2(f[12], f[13]); s1.w = pack_h2(f[14], f[15]);
+      *reinterpret_cast<uint4*>(orow + c0) = s0;
+      *reinterpret_cast<uint4*>(orow + c0 + 8) = s1;
+    }
+    tc_fence_before();
+
+    // ---- guidance loss: the last CTA of this (image, head) reduces (P columns were published before phase 2)
+    if (p.has_loss) {
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        const int old = atomicAdd(&p.L.counters[bh], 1);
+        *s_flag = (old == p.tiles_per_img - 1);
+        if (old == p.tiles_per_img - 1) p.L.counters[bh] = 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_flag) {
+        __threadfence();
+        xattn_loss_reduce(p.L, reinterpret_cast<float*>(sK), s_red, tid, b, h, 8, bh, p.n);
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();   // nobody exits while a peer can still multicast into it or arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace b200

@@ -179,3 +179,24 @@ def xattn_fwd(q, k, vt, B, heads, nq, nk, d, scale, loss=None, want_probs=False,
                                       _i(B), _i(heads), _i(nq), _i(nk), _i(q.shape[1]), _i(k.shape[1]), _i(d),
                                       _f(scale), cur_stream()))
     return out, lse, probs, ptok
+
+
+def xattn_fused_supported(heads, d, n):
+    return bool(lib().b200lmd_xattn_fused_supported(_i(heads), _i(d), _i(n)))
+
+
+def xattn_fused(x, wq, k, vt, wo, bias_o, residual, B, n, heads, d, nk, scale, loss=None, want_probs=False,
+                save_tok=None, want_q=False):
+    """whole cross-attention op (projections + attention + loss) in one launch; x [B*n, C]"""
+    C = heads * d
+    out = torch.empty(B * n, C, device=x.device, dtype=torch.float16)
+    o_scr = torch.empty(B * n, C, device=x.device, dtype=torch.float16)
+    q = torch.zeros(B * heads, n, round_dp(d), device=x.device, dtype=torch.float16) if want_q else None
+    lse = torch.zeros(B * heads, n, device=x.device, dtype=torch.float32) if want_q else None
+    probs = torch.empty(B * heads, n, nk, device=x.device, dtype=torch.float16) if want_probs else None
+    ptok = torch.zeros(B * heads, n, device=x.device, dtype=torch.float16) if save_tok is not None else None
+    check(lib().b200lmd_xattn_fused_f16(ptr(x), ptr(wq), ptr(k), ptr(vt), ptr(wo), ptr(bias_o), ptr(residual), ptr(out),
+                                        ptr(o_scr), ptr(q), ptr(lse), ptr(probs), ptr(save_tok), ptr(ptok),
+                                        ctypes.byref(loss.c) if loss is not None else None, _i(B), _i(n), _i(heads),
+                                        _i(d), _i(nk), _i(k.shape[1]), _f(scale), cur_stream()))
+    return out, q, lse, probs, ptok
