@@ -43,7 +43,7 @@ struct AttnDqCfg {
 };
 
 template <int DPB, int D16, int KVT, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmKt, const __grid_constant__ AttnBwdParams p) {
@@ -81,8 +81,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(&kv_empty[s], 1);
       }
       mbar_init(sdp_full, 1);
-      mbar_init(sdp_empty, 4);
-      mbar_init(ds_full, 4);
+      mbar_init(sdp_empty, 8);   // eight softmax warps: two per TMEM lane quadrant, each takes half the key columns
+      mbar_init(ds_full, 8);
       mbar_init(ds_empty, 1);
       mbar_init(dq_full, 1);
       fence_barrier_init();
@@ -178,6 +178,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;          // column half handled by this warp in pass B
     const int r = quad * 32 + lane_id();
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int qrow = qt * 128 + r;
@@ -217,7 +218,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       mbar_wait(ds_empty, (j & 1) ^ 1);
 #pragma unroll 1
-      for (int c0 = 0; c0 < KVT; c0 += 32) {
+      for (int c0 = grp * (KVT / 2); c0 < (grp + 1) * (KVT / 2); c0 += 32) {
         uint32_t s[32], g[32];
         tmem_ld_x32(tS + lane_off + c0, s);
         if (p.has_dO) tmem_ld_x32(tdP + lane_off + c0, g);
@@ -260,7 +261,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int b = bh / p.heads, h = bh % p.heads;
     __half* orow = p.dq + ((long long)b * p.nq + qrow) * p.ld_dq + h * p.d;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D16; c0 += 16) {
+    for (int c0 = grp * 16; c0 < D16; c0 += 32) {   // the two warps of a quadrant interleave 16-column chunks
       uint32_t v[16];
       tmem_ld_x16(tdQ + lane_off + c0, v);
       tmem_ld_wait();
@@ -300,7 +301,7 @@ struct AttnDkvCfg {
 };
 
 template <int DPB, int D16, int QT, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmdOt,
@@ -339,8 +340,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         mbar_init(&q_empty[s], 1);
       }
       mbar_init(sdp_full, 1);
-      mbar_init(sdp_empty, 4);
-      mbar_init(pt_full, 4);
+      mbar_init(sdp_empty, 8);
+      mbar_init(pt_full, 8);
       mbar_init(pt_empty, 1);
       mbar_init(out_full, 1);
       fence_barrier_init();
@@ -437,8 +438,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
   } else {
     const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;   // column half (query columns) of this warp
     const int r = quad * 32 + lane_id();
-    const int tid = threadIdx.x - 64;  // 0..127 among the softmax warps
+    const int tid = threadIdx.x - 64;  // 0..255 among the softmax warps
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int krow = kt * 128 + r;
     const bool kok = krow < p.nk;
@@ -450,12 +452,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         L[tid] = q < p.nq ? p.lse2[(long long)bh * p.nq_alloc + q] : 0.f;
         Dd[tid] = q < p.nq ? p.delta[(long long)bh * p.nq_alloc + q] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, i & 1);
       mbar_wait(pt_empty, (i & 1) ^ 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < QT; c0 += 32) {
+      for (int c0 = grp * (QT / 2); c0 < (grp + 1) * (QT / 2); c0 += 32) {
         uint32_t s[32], g[32];
         tmem_ld_x32(tST + lane_off + c0, s);
         tmem_ld_x32(tdPT + lane_off + c0, g);
@@ -502,7 +504,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const int b = bh / p.heads, h = bh % p.heads;
     const bool st_ok = krow < p.nk_store;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    for (int which = grp; which < 2; which += 2) {   // warp group 0 drains dV, group 1 drains dK
       __half* base = which ? p.dk : p.dv;
       const int ld = which ? p.ld_dk : p.ld_dv;
       const uint32_t t = which ? tdK : tdV;

@@ -166,7 +166,7 @@ inline void launch_dq_t(const AttnDqLaunch& L, cudaStream_t st) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     done = true;
   }
-  attn_bwd_dq_kernel<DPB, D16, KVT, STAGES><<<L.grid, 192, Cfg::SMEM_BYTES, st>>>(L.tmQ, L.tmdO, L.tmK, L.tmV, L.tmKt,
+  attn_bwd_dq_kernel<DPB, D16, KVT, STAGES><<<L.grid, 320, Cfg::SMEM_BYTES, st>>>(L.tmQ, L.tmdO, L.tmK, L.tmV, L.tmKt,
                                                                                  L.p);
   B200_CHECK(cudaGetLastError());
 }
@@ -218,7 +218,7 @@ inline void launch_dkv_t(const AttnDkvLaunch& L, cudaStream_t st) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     done = true;
   }
-  attn_bwd_dkv_kernel<DPB, D16, QT, STAGES><<<L.grid, 192, Cfg::SMEM_BYTES, st>>>(L.tmK, L.tmV, L.tmQ, L.tmdO, L.tmQt,
+  attn_bwd_dkv_kernel<DPB, D16, QT, STAGES><<<L.grid, 320, Cfg::SMEM_BYTES, st>>>(L.tmK, L.tmV, L.tmQ, L.tmdO, L.tmQt,
                                                                                  L.tmdOt, L.p);
   B200_CHECK(cudaGetLastError());
 }

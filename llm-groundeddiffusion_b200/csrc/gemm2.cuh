@@ -1,0 +1,324 @@
+// Implicit GEMM, second generation: persistent CTAs, double-buffered TMEM accumulators, coalesced epilogue.
+//
+// Why (profiles/bench_kernels.py on B200, round 1): the first kernel's epilogue wrote 16 bytes per thread per row, i.e.
+// 32 different cache lines per warp store; the LSU serialised them (~19 k cycles per 128x128 tile for the K=320 GEGLU
+// projection = 160 TFLOP/s, an HBM-bound op running at 1/20 of its bandwidth bound).  Here
+//   * each CTA loops over output tiles (grid = min(#tiles, #SMs)); while the epilogue warps drain accumulator i from
+//     TMEM, the MMA warp already fills accumulator i^1 for the next tile;
+//   * the epilogue goes through a padded shared-memory staging tile in 64-column chunks: residual / accumulate
+//     operands are loaded into it with full 128-byte row segments, every thread then owns one row (TMEM lane) for the
+//     arithmetic, and the fp16 results leave again as full row segments (4 rows per warp store).
+// Same GemmParams / tensor maps / modes as gemm.cuh (which remains for fp32 outputs and tiny N).
+#pragma once
+#include "gemm.cuh"
+
+namespace b200 {
+
+template <int BLOCK_N>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = 16384;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STG_LD = 72;                        // staging row stride in halves (144 B: conflict-free 16 B rows)
+  static constexpr int STG_BYTES = 128 * STG_LD * 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 128 * 8 + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "smem budget");
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ GemmParams p, int m_tiles, int n_tiles) {
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int LD = Cfg::STG_LD;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __half* stg = reinterpret_cast<__half*>(smem + STAGES * Cfg::STAGE_BYTES);
+  long long* s_orow = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(stg) + Cfg::STG_BYTES);  // [128]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_orow + 128);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // 2
+  uint64_t* tmem_empty = tmem_full + 2;       // 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int total_tiles = m_tiles * n_tiles;
+  const int cpb = (p.Cin + 63) >> 6;
+  const int num_kb = cpb * p.ntaps;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full[s], 1);
+        mbar_init(&tmem_empty[s], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto tile_coords = [&](int tile, int& n0, int& x0, int& y0, int& b0) {
+    const int n_tile = tile % n_tiles;
+    const int m_tile = tile / n_tiles;
+    n0 = n_tile * BLOCK_N;
+    x0 = (m_tile % p.tiles_x) * p.tw;
+    y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
+    b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tb;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, x0, y0, b0;
+        tile_coords(tile, n0, x0, y0, b0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cpb;
+          const int cc = kb - tap * cpb;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const GemmTap t = p.taps[tap];
+          tma_load_4d(sa, &tmA, &full_bar[stage], cc * 64, x0 + t.dx, y0 + t.dy, b0 + t.db);
+          tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], cc * 64, t.wtap, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ab * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_desc_k_sw128(sa);
+          const uint64_t bdesc = make_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          tc_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) tc_commit(&tmem_full[ab]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane_id();      // row in tile == TMEM lane
+    const int tid = threadIdx.x - 64;         // 0..127
+    const int ewarp = tid >> 5;               // 0..3 (row group for the coalesced passes)
+    const int lane = lane_id();
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    __half* my = stg + r * LD;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      int n0, x0, y0, b0;
+      tile_coords(tile, n0, x0, y0, b0);
+      const int n_tile = tile % n_tiles;
+      // row -> output row index (same brick mapping as the producer)
+      const int xl = r % p.tw, yl = (r / p.tw) % p.th, bl = r / (p.tw * p.th);
+      const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
+      const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
+      const long long orow = ((long long)b * p.OH + (y * p.sy + p.oy)) * p.OW + (x * p.sx + p.ox);
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's staging reads are finished
+      s_orow[r] = row_ok ? orow : -1;
+      const int img = p.rows_per_img > 0 ? (int)(orow / p.rows_per_img) : 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // s_orow visible
+      // coalesced passes: warp ew handles rows ew*32 .. +31, 4 rows per instruction (8 lanes x 16 B per row)
+      long long orws[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) orws[rr] = s_orow[ewarp * 32 + rr * 4 + (lane >> 3)];
+      auto for_pieces = [&](auto&& fn) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) fn(ewarp * 32 + rr * 4 + (lane >> 3), lane & 7, orws[rr]);
+      };
+      // residual / accumulate operand: fetched one chunk ahead into registers so its latency hides behind the
+      // accumulator wait and the previous chunk's arithmetic
+      const bool rd = (p.mode == EPI_ROWMAJOR) && ((p.residual != nullptr) || p.accumulate_out);
+      const __half* rsrc = p.residual ? p.residual : p.out;
+      const int rlds = p.residual ? p.ldr : p.ldo;
+      uint4 pre[8];
+      auto load_res = [&](int nb) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int n = nb + (lane & 7) * 8;
+          pre[rr] = (orws[rr] >= 0 && n + 8 <= p.N) ? *reinterpret_cast<const uint4*>(rsrc + orws[rr] * rlds + n)
+                                                    : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (rd) load_res(n0);
+      mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * BLOCK_N + lane_off;
+
+      if (p.mode == EPI_GEGLU) {
+        if constexpr (BLOCK_N == 128) {
+          // 64 outputs per tile: value columns [0,64), gate columns [64,128)
+          uint32_t vv[32], gg[32];
+#pragma unroll 1
+          for (int hc = 0; hc < 2; ++hc) {
+            tmem_ld_x32(taddr + hc * 32, vv);
+            tmem_ld_x32(taddr + 64 + hc * 32, gg);
+            tmem_ld_wait();
+            uint32_t o[16], pv[16], pg[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a0 = __uint_as_float(vv[2 * j]), a1 = __uint_as_float(vv[2 * j + 1]);
+              float g0 = __uint_as_float(gg[2 * j]), g1 = __uint_as_float(gg[2 * j + 1]);
+              if (p.bias) {
+                a0 += __ldg(p.bias + n0 + hc * 32 + 2 * j);
+                a1 += __ldg(p.bias + n0 + hc * 32 + 2 * j + 1);
+                g0 += __ldg(p.bias + n0 + 64 + hc * 32 + 2 * j);
+                g1 += __ldg(p.bias + n0 + 64 + hc * 32 + 2 * j + 1);
+              }
+              o[j] = pack_h2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+              pv[j] = pack_h2(a0, a1);
+              pg[j] = pack_h2(g0, g1);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(my + hc * 32 + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            if (p.pre && row_ok) {   // pre-activation dump (guidance forward only): direct, 64 B runs per row
+              __half* pr = p.pre + orow * (long long)(2 * p.ldo) + n0 + hc * 32;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                *reinterpret_cast<uint4*>(pr + q * 8) = make_uint4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
+                *reinterpret_cast<uint4*>(pr + 64 + q * 8) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for_pieces([&](int row, int pc, long long orw) {
+            if (orw >= 0)
+              *reinterpret_cast<uint4*>(p.out + orw * p.ldo + n_tile * 64 + pc * 8) =
+                  *reinterpret_cast<const uint4*>(stg + row * LD + pc * 8);
+          });
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+          if (n0 + c0 >= p.N) break;
+          const int nb = n0 + c0;                          // first output column of this chunk
+          if (c0 > 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging free again
+          if (rd) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr)
+              *reinterpret_cast<uint4*>(stg + (ewarp * 32 + rr * 4 + (lane >> 3)) * LD + (lane & 7) * 8) = pre[rr];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (c0 + 64 < BLOCK_N && nb + 64 < p.N) load_res(nb + 64);
+          }
+          uint32_t v[64];
+          tmem_ld_x32(taddr + c0, v);
+          tmem_ld_x32(taddr + c0 + 32, v + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = __uint_as_float(v[g * 8 + j]) * p.alpha;
+              const int nn = nb + g * 8 + j;
+              if (nn < p.N) {
+                if (p.bias) a += __ldg(p.bias + nn);
+                if (p.chan_add) a += __ldg(p.chan_add + (long long)img * p.N + nn);
+              }
+              f[j] = a;
+            }
+            if (rd) {
+              uint4 rr = *reinterpret_cast<const uint4*>(my + g * 8);
+              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 t2 = __half22float2(rh[j]);
+                f[2 * j] += t2.x;
+                f[2 * j + 1] += t2.y;
+              }
+            }
+            *reinterpret_cast<uint4*>(my + g * 8) =
+                make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          }
+          if (p.mode == EPI_HEADS) {
+            // transposed slabs: this thread's row is one token, lanes of a warp are consecutive tokens -> coalesced
+            const int tok = (int)(orow % p.rows_per_img);
+            if (row_ok) {
+#pragma unroll 1
+              for (int g = 0; g < 8; ++g) {
+                const int n = nb + g * 8;
+                if (n >= p.N) break;
+                const int which = p.which0 + n / p.C;
+                if (!p.tr[which]) continue;
+                const int cc = n % p.C, head = cc / p.d, j0 = cc % p.d;
+                __half* dst = p.tr[which] + (((long long)img * p.heads + head) * p.d16 + j0) * (long long)p.tr_alloc[which] + tok;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[(long long)j * p.tr_alloc[which]] = my[g * 8 + j];
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (p.mode == EPI_ROWMAJOR) {
+            const bool vec_ok = (p.ldo % 8 == 0);
+            for_pieces([&](int row, int pc, long long orw) {
+              const int n = nb + pc * 8;
+              if (orw < 0 || n >= p.N) return;
+              const __half* s = stg + row * LD + pc * 8;
+              if (vec_ok && n + 8 <= p.N) {
+                *reinterpret_cast<uint4*>(p.out + orw * p.ldo + n) = *reinterpret_cast<const uint4*>(s);
+              } else {
+                for (int j = 0; j < 8 && n + j < p.N; ++j) p.out[orw * p.ldo + n + j] = s[j];
+              }
+            });
+          } else {  // EPI_HEADS row-major slabs: 16-byte pieces never straddle a head (d % 8 == 0)
+            for_pieces([&](int row, int pc, long long orw) {
+              const int n = nb + pc * 8;
+              if (orw < 0 || n >= p.N) return;
+              const int which = p.which0 + n / p.C;
+              if (!p.rm[which]) return;
+              const int cc = n % p.C, head = cc / p.d, j0 = cc % p.d;
+              const int im = (int)(orw / p.rows_per_img), tok = (int)(orw % p.rows_per_img);
+              *reinterpret_cast<uint4*>(p.rm[which] + (((long long)im * p.heads + head) * p.rm_alloc[which] + tok) * (long long)p.dp + j0) =
+                  *reinterpret_cast<const uint4*>(stg + row * LD + pc * 8);
+            });
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace b200

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "gemm.cuh"
+#include "gemm2.cuh"
 
 namespace b200 {
 
@@ -151,7 +152,40 @@ inline void gemm_set_attr() {
   }
 }
 
+inline bool& gemm_use_v2() {
+  static bool v = true;   // persistent kernel with the coalesced epilogue (gemm2.cuh)
+  return v;
+}
+
+template <int BN>
+inline void launch_gemm2(const GemmLaunch& L, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    B200_CHECK(cudaFuncSetAttribute(gemm2_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Gemm2Cfg<BN>::SMEM_BYTES));
+    done = true;
+  }
+  const int m_tiles = (int)L.grid.y, n_tiles = (int)L.grid.x;
+  const long long total = (long long)m_tiles * n_tiles;
+  const int grid = (int)(total < 148 ? total : 148);
+  gemm2_tc_kernel<BN><<<grid, 192, Gemm2Cfg<BN>::SMEM_BYTES, st>>>(L.tmA, L.tmB, L.p, m_tiles, n_tiles);
+  B200_CHECK(cudaGetLastError());
+}
+
+inline bool gemm2_eligible(const GemmLaunch& L) {
+  const GemmParams& p = L.p;
+  if (!gemm_use_v2() || L.block_n < 128 || p.out_f32 || (p.N % 8)) return false;
+  if (p.mode == EPI_ROWMAJOR) return p.out && (p.ldo % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
+  if (p.mode == EPI_GEGLU) return L.block_n == 128;
+  return true;  // EPI_HEADS
+}
+
 inline void run_gemm(const GemmLaunch& L, cudaStream_t st) {
+  if (gemm2_eligible(L)) {
+    if (L.block_n == 128) launch_gemm2<128>(L, st);
+    else launch_gemm2<256>(L, st);
+    return;
+  }
   switch (L.block_n) {
     case 64:
       gemm_set_attr<64>();

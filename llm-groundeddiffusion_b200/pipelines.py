@@ -77,9 +77,14 @@ class CudaGraph:
     """capture a launch-only callable once (after an eager warm-up run) and replay it; all tensors it touches must be
     static (updated in place between replays)"""
 
-    def __init__(self, fn):
-        fn()                                   # eager warm-up: one-time func attributes, allocator warm-up
-        torch.cuda.synchronize()
+    _warmed = set()
+
+    def __init__(self, fn, key=None):
+        if key is None or key not in CudaGraph._warmed:
+            fn()                               # first use of this launch sequence: eager run (one-time kernel
+            torch.cuda.synchronize()           # attributes, driver entry points, allocator warm-up)
+            if key is not None:
+                CudaGraph._warmed.add(key)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = fn()
@@ -165,7 +170,8 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
         if use_graphs:
             if fuser_on not in state.graphs:
                 state.graphs[fuser_on] = CudaGraph(lambda: net.guidance_gradient_launch(
-                    z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on))
+                    z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on),
+                    key=("guid", id(net), tuple(z.shape), fuser_on, objs is not None))
             grad, parts = state.graphs[fuser_on]()
         else:
             grad, parts = net.guidance_gradient_launch(z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on)
@@ -230,7 +236,8 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
         if use_graphs:
             if fuser_on not in fwd_graphs:
                 fwd_graphs[fuser_on] = CudaGraph(lambda: net.forward(
-                    z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys, save_tok=tok_dev))
+                    z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys, save_tok=tok_dev),
+                    key=("fwd", id(net), tuple(z.shape), fuser_on, objs_main is not None, save_keys is not None))
             eps, saved = fwd_graphs[fuser_on]()
         else:
             eps, saved = net.forward(z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys,

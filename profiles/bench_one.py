@@ -1,0 +1,46 @@
+"""single-kernel driver for ncu --set full captures: python profiles/bench_one.py <case>"""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lgd_b200  # noqa: E402
+from lgd_b200 import ops  # noqa: E402
+from lgd_b200._lib import lib  # noqa: E402
+
+dev = torch.device("cuda:0")
+case = sys.argv[1] if len(sys.argv) > 1 else "proj320"
+torch.manual_seed(0)
+if case == "proj320":
+    M, N, K = 65536, 320, 320
+    x, w, res = torch.randn(M, K, device=dev).half(), torch.randn(N, K, device=dev).half(), torch.randn(M, N, device=dev).half()
+    for _ in range(3):
+        ops.linear(x, w, None, res)
+elif case == "proj320_nores":
+    M, N, K = 65536, 320, 320
+    x, w = torch.randn(M, K, device=dev).half(), torch.randn(N, K, device=dev).half()
+    for _ in range(3):
+        ops.linear(x, w)
+elif case == "toq":
+    M, N, K = 2048, 1280, 1280
+    x, w = torch.randn(M, K, device=dev).half(), torch.randn(N, K, device=dev).half()
+    for _ in range(3):
+        ops.linear(x, w)
+elif case == "conv320":
+    x = torch.randn(16, 64, 64, 320, device=dev).half()
+    w = torch.randn(320, 9, 320, device=dev).half()
+    for _ in range(3):
+        ops.conv3x3(x, w)
+elif case == "attn":
+    B, heads, d, n = 16, 8, 40, 4096
+    q, k, vt = ops.alloc_head_slabs(B, heads, d, n, n, dev)
+    q.normal_(); k.normal_(); vt.normal_()
+    q[:, :, d:] = 0
+    k[:, :, d:] = 0
+    for _ in range(3):
+        ops.attention_fwd(q, k, vt, B, heads, n, n, d, d ** -0.5)
+torch.cuda.synchronize()
+print("done", case)

@@ -11,8 +11,8 @@ def _rel(a, b):
     return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 
 
-@pytest.mark.parametrize("B,d,n,with_loss", [(8, 160, 256, True), (2, 160, 256, False), (3, 64, 128, True),
-                                             (2, 80, 1024, False), (1, 160, 128, True)])
+@pytest.mark.parametrize("B,d,n,with_loss", [(8, 160, 256, True), (2, 160, 256, False), (3, 64, 256, True),
+                                             (2, 80, 1024, False), (1, 160, 256, True)])
 def test_fused_matches_unfused_and_torch(cuda, B, d, n, with_loss):
     from lgd_b200 import guidance as G, ops
     from test_xattn_loss_gpu import _layouts
