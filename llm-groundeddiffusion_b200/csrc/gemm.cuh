@@ -57,7 +57,21 @@ struct GemmParams {
   __half* tr[3]; int tr_alloc[3];   // transposed slab per projection [B*heads, d16, tr_alloc]  (or null)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// exact (erf) GELU, F.gelu default (models/attention.py:329).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below fp16 output resolution): two SFU ops + ~10 FMAs instead of libdevice erff's ~40 instructions - the GEGLU
+// epilogue is issue-bound on the short-K feed-forward GEMMs.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = poly * t * ex2_approx(-z * z * 1.4426950408889634f);   // 1 - erf(z)
+  const float erf_abs = 1.f - e;
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
 
 template <int BLOCK_N>
 struct GemmCfg {

@@ -27,7 +27,7 @@ struct Gemm2Cfg {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmParams p, int m_tiles, int n_tiles) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
@@ -60,7 +60,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full[s], 1);
-        mbar_init(&tmem_empty[s], 4);
+        mbar_init(&tmem_empty[s], 8);
       }
       fence_barrier_init();
     }
@@ -129,46 +129,49 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
+    // ===================== epilogue warps 2..9 =====================
+    // Two warps per TMEM lane quadrant: both own the same 32 rows, each takes 32 of the 64 columns of a chunk, so the
+    // epilogue arithmetic (the bottleneck of the short-K GEMMs) is spread over all four SM sub-partitions twice.
+    const int ew = warp - 2;                  // 0..7
     const int quad = warp & 3;
+    const int half = ew >> 2;                 // column half inside a 64-column chunk
     const int r = quad * 32 + lane_id();      // row in tile == TMEM lane
-    const int tid = threadIdx.x - 64;         // 0..127
-    const int ewarp = tid >> 5;               // 0..3 (row group for the coalesced passes)
     const int lane = lane_id();
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    __half* my = stg + r * LD;
+    const uint32_t stg_s = smem_u32(stg);
+    const uint32_t my_s = stg_s + (r * LD + half * 32) * 2;
+    __half* my = stg + r * LD + half * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
       int n0, x0, y0, b0;
       tile_coords(tile, n0, x0, y0, b0);
       const int n_tile = tile % n_tiles;
-      // row -> output row index (same brick mapping as the producer)
       const int xl = r % p.tw, yl = (r / p.tw) % p.th, bl = r / (p.tw * p.th);
       const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
       const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
       const long long orow = ((long long)b * p.OH + (y * p.sy + p.oy)) * p.OW + (x * p.sx + p.ox);
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's staging reads are finished
-      s_orow[r] = row_ok ? orow : -1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's staging reads are finished
+      if (half == 0) s_orow[r] = row_ok ? orow : -1;
       const int img = p.rows_per_img > 0 ? (int)(orow / p.rows_per_img) : 0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // s_orow visible
-      // coalesced passes: warp ew handles rows ew*32 .. +31, 4 rows per instruction (8 lanes x 16 B per row)
-      long long orws[8];
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // s_orow visible
+      // coalesced passes: warp ew moves rows ew*16 .. +15, 4 rows per instruction (8 lanes x 16 B per row)
+      long long orws[4];
 #pragma unroll
-      for (int rr = 0; rr < 8; ++rr) orws[rr] = s_orow[ewarp * 32 + rr * 4 + (lane >> 3)];
+      for (int rr = 0; rr < 4; ++rr) orws[rr] = s_orow[ew * 16 + rr * 4 + (lane >> 3)];
       auto for_pieces = [&](auto&& fn) {
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) fn(ewarp * 32 + rr * 4 + (lane >> 3), lane & 7, orws[rr]);
+        for (int rr = 0; rr < 4; ++rr) fn(ew * 16 + rr * 4 + (lane >> 3), lane & 7, orws[rr]);
       };
       // residual / accumulate operand: fetched one chunk ahead into registers so its latency hides behind the
       // accumulator wait and the previous chunk's arithmetic
       const bool rd = (p.mode == EPI_ROWMAJOR) && ((p.residual != nullptr) || p.accumulate_out);
       const __half* rsrc = p.residual ? p.residual : p.out;
       const int rlds = p.residual ? p.ldr : p.ldo;
-      uint4 pre[8];
+      uint4 pre[4];
       auto load_res = [&](int nb) {
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
+        for (int rr = 0; rr < 4; ++rr) {
           const int n = nb + (lane & 7) * 8;
           pre[rr] = (orws[rr] >= 0 && n + 8 <= p.N) ? *reinterpret_cast<const uint4*>(rsrc + orws[rr] * rlds + n)
                                                     : make_uint4(0, 0, 0, 0);
@@ -181,45 +184,40 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
       if (p.mode == EPI_GEGLU) {
         if constexpr (BLOCK_N == 128) {
-          // 64 outputs per tile: value columns [0,64), gate columns [64,128)
+          // 64 outputs per tile: value columns [0,64), gate columns [64,128); this thread: 32 of them
           uint32_t vv[32], gg[32];
-#pragma unroll 1
-          for (int hc = 0; hc < 2; ++hc) {
-            tmem_ld_x32(taddr + hc * 32, vv);
-            tmem_ld_x32(taddr + 64 + hc * 32, gg);
-            tmem_ld_wait();
-            uint32_t o[16], pv[16], pg[16];
+          tmem_ld_x32(taddr + half * 32, vv);
+          tmem_ld_x32(taddr + 64 + half * 32, gg);
+          tmem_ld_wait();
+          uint32_t o[16], pv[16], pg[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a0 = __uint_as_float(vv[2 * j]), a1 = __uint_as_float(vv[2 * j + 1]);
-              float g0 = __uint_as_float(gg[2 * j]), g1 = __uint_as_float(gg[2 * j + 1]);
-              if (p.bias) {
-                a0 += __ldg(p.bias + n0 + hc * 32 + 2 * j);
-                a1 += __ldg(p.bias + n0 + hc * 32 + 2 * j + 1);
-                g0 += __ldg(p.bias + n0 + 64 + hc * 32 + 2 * j);
-                g1 += __ldg(p.bias + n0 + 64 + hc * 32 + 2 * j + 1);
-              }
-              o[j] = pack_h2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
-              pv[j] = pack_h2(a0, a1);
-              pg[j] = pack_h2(g0, g1);
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(vv[2 * j]), a1 = __uint_as_float(vv[2 * j + 1]);
+            float g0 = __uint_as_float(gg[2 * j]), g1 = __uint_as_float(gg[2 * j + 1]);
+            if (p.bias) {
+              a0 += __ldg(p.bias + n0 + half * 32 + 2 * j);
+              a1 += __ldg(p.bias + n0 + half * 32 + 2 * j + 1);
+              g0 += __ldg(p.bias + n0 + 64 + half * 32 + 2 * j);
+              g1 += __ldg(p.bias + n0 + 64 + half * 32 + 2 * j + 1);
             }
+            o[j] = pack_h2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+            pv[j] = pack_h2(a0, a1);
+            pg[j] = pack_h2(g0, g1);
+          }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(my + hc * 32 + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-            if (p.pre && row_ok) {   // pre-activation dump (guidance forward only): direct, 64 B runs per row
-              __half* pr = p.pre + orow * (long long)(2 * p.ldo) + n0 + hc * 32;
+          for (int q = 0; q < 4; ++q) sts128(my_s + q * 16, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+          if (p.pre && row_ok) {   // pre-activation dump (guidance forward only): direct, 64 B runs per row
+            __half* pr = p.pre + orow * (long long)(2 * p.ldo) + n0 + half * 32;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                *reinterpret_cast<uint4*>(pr + q * 8) = make_uint4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
-                *reinterpret_cast<uint4*>(pr + 64 + q * 8) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
-              }
+            for (int q = 0; q < 4; ++q) {
+              *reinterpret_cast<uint4*>(pr + q * 8) = make_uint4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
+              *reinterpret_cast<uint4*>(pr + 64 + q * 8) = make_uint4(pg[4 * q], pg[4 * q + 1], pg[4 * q + 2], pg[4 * q + 3]);
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           for_pieces([&](int row, int pc, long long orw) {
             if (orw >= 0)
-              *reinterpret_cast<uint4*>(p.out + orw * p.ldo + n_tile * 64 + pc * 8) =
-                  *reinterpret_cast<const uint4*>(stg + row * LD + pc * 8);
+              *reinterpret_cast<uint4*>(p.out + orw * p.ldo + n_tile * 64 + pc * 8) = lds128(stg_s + (row * LD + pc * 8) * 2);
           });
         }
       } else {
@@ -227,25 +225,25 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
           if (n0 + c0 >= p.N) break;
           const int nb = n0 + c0;                          // first output column of this chunk
-          if (c0 > 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging free again
+          if (c0 > 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // staging free again
           if (rd) {
 #pragma unroll
-            for (int rr = 0; rr < 8; ++rr)
-              *reinterpret_cast<uint4*>(stg + (ewarp * 32 + rr * 4 + (lane >> 3)) * LD + (lane & 7) * 8) = pre[rr];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int rr = 0; rr < 4; ++rr)
+              sts128(stg_s + ((ew * 16 + rr * 4 + (lane >> 3)) * LD + (lane & 7) * 8) * 2, pre[rr]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (c0 + 64 < BLOCK_N && nb + 64 < p.N) load_res(nb + 64);
           }
-          uint32_t v[64];
-          tmem_ld_x32(taddr + c0, v);
-          tmem_ld_x32(taddr + c0 + 32, v + 32);
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c0 + half * 32, v);
           tmem_ld_wait();
+          const int nh = nb + half * 32;                   // first column of this thread's 32
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < 4; ++g) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float a = __uint_as_float(v[g * 8 + j]) * p.alpha;
-              const int nn = nb + g * 8 + j;
+              const int nn = nh + g * 8 + j;
               if (nn < p.N) {
                 if (p.bias) a += __ldg(p.bias + nn);
                 if (p.chan_add) a += __ldg(p.chan_add + (long long)img * p.N + nn);
@@ -253,7 +251,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               f[j] = a;
             }
             if (rd) {
-              uint4 rr = *reinterpret_cast<const uint4*>(my + g * 8);
+              uint4 rr = lds128(my_s + g * 16);
               const __half2* rh = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -262,16 +260,16 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 f[2 * j + 1] += t2.y;
               }
             }
-            *reinterpret_cast<uint4*>(my + g * 8) =
-                make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+            sts128(my_s + g * 16,
+                   make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])));
           }
           if (p.mode == EPI_HEADS) {
             // transposed slabs: this thread's row is one token, lanes of a warp are consecutive tokens -> coalesced
             const int tok = (int)(orow % p.rows_per_img);
             if (row_ok) {
 #pragma unroll 1
-              for (int g = 0; g < 8; ++g) {
-                const int n = nb + g * 8;
+              for (int g = 0; g < 4; ++g) {
+                const int n = nh + g * 8;
                 if (n >= p.N) break;
                 const int which = p.which0 + n / p.C;
                 if (!p.tr[which]) continue;
@@ -282,16 +280,16 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (p.mode == EPI_ROWMAJOR) {
             const bool vec_ok = (p.ldo % 8 == 0);
             for_pieces([&](int row, int pc, long long orw) {
               const int n = nb + pc * 8;
               if (orw < 0 || n >= p.N) return;
-              const __half* s = stg + row * LD + pc * 8;
               if (vec_ok && n + 8 <= p.N) {
-                *reinterpret_cast<uint4*>(p.out + orw * p.ldo + n) = *reinterpret_cast<const uint4*>(s);
+                *reinterpret_cast<uint4*>(p.out + orw * p.ldo + n) = lds128(stg_s + (row * LD + pc * 8) * 2);
               } else {
+                const __half* s = stg + row * LD + pc * 8;
                 for (int j = 0; j < 8 && n + j < p.N; ++j) p.out[orw * p.ldo + n + j] = s[j];
               }
             });
@@ -304,7 +302,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const int cc = n % p.C, head = cc / p.d, j0 = cc % p.d;
               const int im = (int)(orw / p.rows_per_img), tok = (int)(orw % p.rows_per_img);
               *reinterpret_cast<uint4*>(p.rm[which] + (((long long)im * p.heads + head) * p.rm_alloc[which] + tok) * (long long)p.dp + j0) =
-                  *reinterpret_cast<const uint4*>(stg + row * LD + pc * 8);
+                  lds128(stg_s + (row * LD + pc * 8) * 2);
             });
           }
         }

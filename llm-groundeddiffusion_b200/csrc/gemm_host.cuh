@@ -168,7 +168,7 @@ inline void launch_gemm2(const GemmLaunch& L, cudaStream_t st) {
   const int m_tiles = (int)L.grid.y, n_tiles = (int)L.grid.x;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = (int)(total < 148 ? total : 148);
-  gemm2_tc_kernel<BN><<<grid, 192, Gemm2Cfg<BN>::SMEM_BYTES, st>>>(L.tmA, L.tmB, L.p, m_tiles, n_tiles);
+  gemm2_tc_kernel<BN><<<grid, 320, Gemm2Cfg<BN>::SMEM_BYTES, st>>>(L.tmA, L.tmB, L.p, m_tiles, n_tiles);
   B200_CHECK(cudaGetLastError());
 }
 

@@ -186,6 +186,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// two 2^x per SFU op on a packed fp16 pair (result packed fp16x2)
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t xh2) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(xh2));
+  return y;
+}
+
+// explicit shared-space 16-byte accesses (the compiler otherwise falls back to generic ST.E / LD.E for pointers it
+// derives from the dynamic shared-memory base)
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a K-major SW128 tile (128-byte rows)
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return row * 128u + ((chunk ^ (row & 7u)) << 4);

@@ -131,6 +131,8 @@ class B200UNet:
         self.gscale = float(grad_scale)
         self.w: Dict[str, torch.Tensor] = {}
         self._prepare(weights)
+        self.use_fused_xattn = True
+        self._slab_cache: Dict[tuple, torch.Tensor] = {}
         self.tape: Optional[list] = None
         self.grads: Dict[int, torch.Tensor] = {}
         self._keep: list = []
@@ -390,10 +392,22 @@ class B200UNet:
         return self.linear(h, prefix + ".net.2", residual=residual, alpha=alpha, bias=out_bias)
 
     # ------------------------------------------------------------------------------------------ attention
-    def _slabs(self, BH, n_alloc, d, rm=True, tr=True):
+    def _slabs(self, BH, n_alloc, d, rm=True, tr=True, slot=None):
+        """attention operand slabs.  Padding (columns d..dp, rows d..d16) must be zero and is never written, so in
+        forward-only mode (no tape) the zero-filled buffers are cached per (shape, slot) and reused by every layer and
+        step - stream order serialises the layers - instead of memset-ing ~1 GB per attention layer at batch 64."""
         dp, d16 = ops.round_dp(d), ops.round_d16(d)
-        a = torch.zeros(BH, n_alloc, dp, device=self.dev, dtype=torch.float16) if rm else None
-        b = torch.zeros(BH, d16, n_alloc, device=self.dev, dtype=torch.float16) if tr else None
+
+        def get(kind, shape):
+            if self.tape is not None or slot is None:
+                return torch.zeros(shape, device=self.dev, dtype=torch.float16)
+            key = (kind, slot) + tuple(shape)
+            t = self._slab_cache.get(key)
+            if t is None:
+                t = self._slab_cache[key] = torch.zeros(shape, device=self.dev, dtype=torch.float16)
+            return t
+        a = get("rm", (BH, n_alloc, dp)) if rm else None
+        b = get("tr", (BH, d16, n_alloc)) if tr else None
         return a, b
 
     def self_attention(self, xn, B, n, prefix, heads, residual, alpha=1.0, out_bias=None, nk_store=None):
@@ -402,9 +416,9 @@ class B200UNet:
         d = C // heads
         rec = self.tape is not None
         na = (n + 7) // 8 * 8
-        q, qt = self._slabs(B * heads, na, d, True, rec)
-        k, kt = self._slabs(B * heads, na, d, True, rec)
-        v, vt = self._slabs(B * heads, na, d, rec, True)
+        q, qt = self._slabs(B * heads, na, d, True, rec, slot="q")
+        k, kt = self._slabs(B * heads, na, d, True, rec, slot="k")
+        v, vt = self._slabs(B * heads, na, d, rec, True, slot="v")
         M = B * n
         gemm(xn, (1, 1, M, C, C), self.w[prefix + ".qkv.w"], 3 * C, 1, (1, 1, M), TAPS_1x1, mode=2, rows_per_img=n,
              heads=heads, head_dim=d, which0=0, rm=(q, k, v), tr=(qt, kt, vt))
@@ -455,20 +469,32 @@ class B200UNet:
         M = B * n
         k, v, kt, vt = kv
         T = self.text_T
-        q, _ = self._slabs(B * heads, na, d, True, False)
-        gemm(xn, (1, 1, M, C, C), self.w[prefix + ".to_q.w"], C, 1, (1, 1, M), TAPS_1x1, mode=2, rows_per_img=n,
-             heads=heads, head_dim=d, which0=0, rm=(q, None, None))
         scale = d ** -0.5
-        o = torch.empty(M, C, device=self.dev, dtype=torch.float16)
-        lse = torch.zeros(B * heads, na, device=self.dev, dtype=torch.float32) if rec else None
         want_probs = bool(save and save.get("probs"))
         tok = save.get("tok") if save else None
         probs = torch.empty(B * heads, n, T, device=self.dev, dtype=torch.float16) if want_probs else None
         ptok = torch.zeros(B * heads, n, device=self.dev, dtype=torch.float16) if tok is not None else None
-        check(lib().b200lmd_xattn_fwd_f16(ptr(q), ptr(k), ptr(vt), ptr(o), _i(C), ptr(lse), ptr(probs), ptr(tok),
-                                          ptr(ptok), ctypes.byref(loss.c) if loss is not None else None, _i(B),
-                                          _i(heads), _i(n), _i(T), _i(na), _i(k.shape[1]), _i(d), _f(scale),
-                                          cur_stream()))
+        lse = torch.zeros(B * heads, na, device=self.dev, dtype=torch.float32) if rec else None
+        fused = self.use_fused_xattn and T <= 80 and k.shape[1] >= 80 and ops.xattn_fused_supported(heads, d, n)
+        if fused:
+            # whole op in ONE launch (csrc/xattn_fused.cuh): to_q, QK^T, softmax, loss, PV, to_out + bias + residual
+            q = torch.zeros(B * heads, na, ops.round_dp(d), device=self.dev, dtype=torch.float16) if rec else None
+            y = torch.empty(M, C, device=self.dev, dtype=torch.float16)
+            o = torch.empty(M, C, device=self.dev, dtype=torch.float16)
+            check(lib().b200lmd_xattn_fused_f16(
+                ptr(xn), ptr(self.w[prefix + ".to_q.w"]), ptr(k), ptr(vt), ptr(self.w[prefix + ".to_out.0.w"]),
+                ptr(self.w[prefix + ".to_out.0.bias"]), ptr(residual), ptr(y), ptr(o), ptr(q), ptr(lse), ptr(probs),
+                ptr(tok), ptr(ptok), ctypes.byref(loss.c) if loss is not None else None, _i(B), _i(n), _i(heads),
+                _i(d), _i(T), _i(k.shape[1]), _f(scale), cur_stream()))
+        else:
+            q, _ = self._slabs(B * heads, na, d, True, False, slot="xq")
+            gemm(xn, (1, 1, M, C, C), self.w[prefix + ".to_q.w"], C, 1, (1, 1, M), TAPS_1x1, mode=2, rows_per_img=n,
+                 heads=heads, head_dim=d, which0=0, rm=(q, None, None))
+            o = torch.empty(M, C, device=self.dev, dtype=torch.float16)
+            check(lib().b200lmd_xattn_fwd_f16(ptr(q), ptr(k), ptr(vt), ptr(o), _i(C), ptr(lse), ptr(probs), ptr(tok),
+                                              ptr(ptok), ctypes.byref(loss.c) if loss is not None else None, _i(B),
+                                              _i(heads), _i(n), _i(T), _i(na), _i(k.shape[1]), _i(d), _f(scale),
+                                              cur_stream()))
         if save is not None:
             save["out"][key] = dict(probs=probs.view(B, heads, n, T) if probs is not None else None,
                                     tok=ptok.view(B, heads, n) if ptok is not None else None)
@@ -478,10 +504,11 @@ class B200UNet:
                 self._rec(lambda: self._xattn_bwd(xn, q, k, v, kt, None, lse, loss, B, heads, n, na, d, scale, prefix,
                                                   C, M))
             raise _Truncate()
-        y = self.linear(o, prefix + ".to_out.0", residual=residual)
+        if not fused:
+            y = self.linear(o, prefix + ".to_out.0", residual=residual)
+            if rec:
+                self.tape.pop()
         if rec:
-            self.tape.pop()
-
             def bwd():
                 dyv = self._grad_of(y)
                 if dyv is None and loss is None:

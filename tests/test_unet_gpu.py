@@ -90,3 +90,39 @@ def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref):
         r = _rel(grad[b:b + 1], gref)
         print('image', b, 'loss', float(loss[b]), float(L), 'grad rel-L2', r)
         assert r < 8e-2, r
+
+
+def test_guidance_gradient_fused_xattn_path(cuda):
+    """64x64 latents: up-block-1 maps have n = 256 tokens, head_dim 64 -> the single-launch xattn_fused_kernel is used
+    inside the network (forward + its backward through the stored Q / row statistics)."""
+    from lgd_b200 import guidance as G, ops
+    from oracle import guidance_ref, unet_ref
+    B, side, heads = 1, 64, 8
+    ocfg, w, net, z, uncond, cond = _setup(False, B, side, seed=5)
+    assert ops.xattn_fused_supported(heads, 64, 256)
+    kv = net.set_text(torch.cat([uncond, cond], 0))
+    lay = [G.SampleLayout([[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9)]], [[2, 3], [6]], [3, 6])]
+    params = G.LossParams(loss_scale=5.0, fg_weight=1.0, bg_weight=4.0)
+    slot_tok, slot_of = G.assign_slots(lay, params)
+    slot_dev = torch.from_numpy(slot_tok).to(cuda)
+    losses = {k: G.KeyLoss(lay, slot_dev, slot_of, k, 64 if k[0] == "mid" else 256, heads, len(KEYS), params, cuda,
+                           gscale=net.gscale) for k in KEYS}
+    t = torch.full((B,), 621.0, device=cuda)
+    kv_cond = lambda p: tuple(s[B * heads:] for s in kv.slabs[p])
+    grads = {}
+    for fused in (True, False):
+        net.use_fused_xattn = fused
+        g, loss = net.guidance_gradient(z.to(cuda), t, kv_cond, losses)
+        torch.cuda.synchronize()
+        grads[fused] = ((g.view(B, side, side, 8)[..., :4].permute(0, 3, 1, 2) / net.gscale).cpu(), loss.copy())
+    assert _rel(grads[True][0], grads[False][0]) < 2e-2
+    zz = z[:1].clone().requires_grad_(True)
+    saved = {}
+    unet_ref.unet_forward(w, ocfg, zz, 621, cond[:1], saved=saved, save_keys=KEYS)
+    L = guidance_ref.ca_loss({k: v[0] for k, v in saved.items()}, lay[0].bboxes, lay[0].object_positions, KEYS, 0.2, 0.2,
+                             1.0, 4.0) * 5.0
+    gref = torch.autograd.grad(L, [zz])[0]
+    r = _rel(grads[True][0], gref)
+    print("fused path: loss", float(grads[True][1][0]), float(L), "grad rel-L2", r)
+    assert abs(float(grads[True][1][0]) - float(L)) < 2e-2 * abs(float(L))
+    assert r < 8e-2, r
