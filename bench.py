@@ -91,7 +91,7 @@ def peaks():
 XATTN_DRAM_BYTES_NCU = None
 
 
-def xattn_roofline(dev):
+def xattn_roofline(dev, with_loss=True):
     """the fused cross-attention+loss kernel at the config's guidance shape (B=8, n=256, C=1280, heads 8, T=77):
     algorithmic FLOPs 2nC^2 (to_q) + 2nTC (QK^T) + 2nTC (PV) + 2nC^2 (to_out) per sample, one
     launch, timed with CUDA events around a graph replay of that single kernel, L2 flushed between repetitions."""
@@ -127,7 +127,7 @@ def xattn_roofline(dev):
     res = x.clone()
 
     def op():      # ONE launch: xattn_fused_kernel (to_q, QK^T, softmax, loss + dP, PV, to_out + bias + residual)
-        return ops.xattn_fused(x, wq, k, vt, wo, bo, res, B, n, heads, d, T, d ** -0.5, loss=kl)[0]
+        return ops.xattn_fused(x, wq, k, vt, wo, bo, res, B, n, heads, d, T, d ** -0.5, loss=kl if with_loss else None)[0]
 
     for _ in range(3):
         op()

@@ -18,7 +18,7 @@ inline XattnLaunch build_xattn(const __half* q, const __half* k, const __half* v
   XattnLaunch L;
   memset(&L, 0, sizeof(L));
   if (nk > 128) throw std::runtime_error("xattn: at most 128 keys");
-  if (loss && nq > 4096) throw std::runtime_error("xattn loss: at most 4096 query tokens per image");
+  if (loss && nq > 1536) throw std::runtime_error("xattn loss: at most 1536 query tokens per image");
   const int dp = round_dp(d), d16 = round_d16(d), BH = B * heads;
   L.dpb = dp / 64; L.d16 = d16;
   L.tmQ = slab_rm_map(q, BH, nq_alloc, dp, 128);
@@ -115,6 +115,7 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     using namespace b200;
     if (!b200lmd_xattn_fused_supported(heads, head_dim, n)) throw std::runtime_error("xattn_fused: unsupported shape");
     if (nk > 80 || k_alloc < 80) throw std::runtime_error("xattn_fused: needs <= 80 text keys in 80-row slabs");
+    if (loss && n > 1536) throw std::runtime_error("xattn loss: at most 1536 query tokens per image");
     const int C = heads * head_dim;
     const long long M = (long long)B * n;
     const int dp = round_dp(head_dim), d16 = round_d16(head_dim);

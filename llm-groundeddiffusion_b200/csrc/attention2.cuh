@@ -204,9 +204,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         m_ref = m_new;
-        // ---- P = 2^(s' - m_ref) -> fp16 smem, row sum.  The exponential runs on packed fp16 pairs
-        // (ex2.approx.ftz.f16x2: two results per SFU op; P is stored in fp16 anyway, and the row sum is formed from the
-        // SAME rounded values that multiply V, in fp16x2 over 16 elements and fp32 beyond)
+        // ---- P = 2^(s' - m_ref) -> fp16 smem, row sum
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -215,24 +213,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
-          for (int hblk = 0; hblk < 2; ++hblk) {
-            __half2 acc2 = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) {
-              const int i = hblk * 8 + ii;
-              const float x0 = fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_ref);
-              const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_ref);
-              uint32_t e = ex2_f16x2(pack_h2(x0, x1));
-              if (!full) {
-                if (kbase + c0 + 2 * i >= p.nk) e &= 0xFFFF0000u;
-                if (kbase + c0 + 2 * i + 1 >= p.nk) e &= 0x0000FFFFu;
-              }
-              pk[i] = e;
-              acc2 = __hadd2(acc2, *reinterpret_cast<const __half2*>(&e));
+          for (int i = 0; i < 16; ++i) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_ref));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_ref));
+            if (!full) {
+              if (kbase + c0 + 2 * i >= p.nk) e0 = 0.f;
+              if (kbase + c0 + 2 * i + 1 >= p.nk) e1 = 0.f;
             }
-            const float2 f2 = __half22float2(acc2);
-            a0 += f2.x;
-            a1 += f2.y;
+            a0 += e0;
+            a1 += e1;
+            pk[i] = pack_h2(e0, e1);
           }
           uint8_t* atom = sPt + (c0 >> 6) * 16384;
           const int ch0 = (c0 & 63) >> 3;

@@ -7,6 +7,7 @@
 
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gemm3.cuh"
 
 namespace b200 {
 
@@ -172,6 +173,48 @@ inline void launch_gemm2(const GemmLaunch& L, cudaStream_t st) {
   B200_CHECK(cudaGetLastError());
 }
 
+inline bool& gemm_use_v3() {
+  static bool v = true;   // TMA-only epilogue (gemm3.cuh) for row-major fp16 outputs
+  return v;
+}
+
+inline bool gemm3_eligible(const GemmLaunch& L) {
+  const GemmParams& p = L.p;
+  // measured (profiles/bench_kernels.py): the TMA epilogue wins on short contractions (K=320: 80 -> 56 us), while long
+  // ones prefer the deeper smem pipeline of gemm2 (conv 3x3: 147 vs 153 us)
+  const int num_kb = ((p.Cin + 63) / 64) * p.ntaps;
+  if (num_kb > 10) return false;
+  return gemm_use_v3() && L.block_n >= 128 && p.mode == EPI_ROWMAJOR && p.out && !p.out_f32 && (p.N % 8 == 0) &&
+         (p.ldo % 8 == 0) && p.sy == 1 && p.sx == 1 && p.oy == 0 && p.ox == 0 && p.OH == p.H && p.OW == p.W &&
+         (!p.residual || p.ldr % 8 == 0) && !(p.residual && p.accumulate_out);
+}
+
+// 4-D view (N, W, H, B) of a row-major [rows, ld] tensor whose rows enumerate the output-pixel grid
+inline CUtensorMap out_tile_map(const __half* base, int ld, const GemmParams& p) {
+  uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * p.W, (uint64_t)ld * 2 * p.W * p.H};
+  uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tb};
+  return make_tmap_f16(base, 4, dims, strides, box);
+}
+
+template <int BN>
+inline void launch_gemm3(const GemmLaunch& L, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    B200_CHECK(cudaFuncSetAttribute(gemm3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Gemm3Cfg<BN>::SMEM_BYTES));
+    done = true;
+  }
+  const GemmParams& p = L.p;
+  const CUtensorMap tmC = out_tile_map(p.out, p.ldo, p);
+  const CUtensorMap tmR = p.residual ? out_tile_map(p.residual, p.ldr, p) : tmC;   // accumulate: re-read the output
+  const int m_tiles = (int)L.grid.y, n_tiles = (int)L.grid.x;
+  const long long total = (long long)m_tiles * n_tiles;
+  const int grid = (int)(total < 148 ? total : 148);
+  gemm3_tc_kernel<BN><<<grid, 320, Gemm3Cfg<BN>::SMEM_BYTES, st>>>(L.tmA, L.tmB, tmC, tmR, L.p, m_tiles, n_tiles);
+  B200_CHECK(cudaGetLastError());
+}
+
 inline bool gemm2_eligible(const GemmLaunch& L) {
   const GemmParams& p = L.p;
   if (!gemm_use_v2() || L.block_n < 128 || p.out_f32 || (p.N % 8)) return false;
@@ -181,6 +224,11 @@ inline bool gemm2_eligible(const GemmLaunch& L) {
 }
 
 inline void run_gemm(const GemmLaunch& L, cudaStream_t st) {
+  if (gemm3_eligible(L)) {
+    if (L.block_n == 128) launch_gemm3<128>(L, st);
+    else launch_gemm3<256>(L, st);
+    return;
+  }
   if (gemm2_eligible(L)) {
     if (L.block_n == 128) launch_gemm2<128>(L, st);
     else launch_gemm2<256>(L, st);

@@ -77,79 +77,131 @@ __device__ __forceinline__ float block128_sum(float v, float* red, int tid) {
 
 
 // Loss / gradient of one (image, head) from the published P columns (utils/guidance.py:91-242).  Called by the 128
-// softmax threads of the last CTA of that (image, head); scratch: >= 2n floats of shared memory.
+// softmax threads (4 warps) of the last CTA of that (image, head); scratch: >= 4*n + 160 floats of shared memory (n <= 1536 with the callers' buffers).
+//
+// Work is split into independent "problems", one warp each (round-robin): an energy term contributes two top-k
+// selections (foreground / background), a reference term one normalised-L1.  Top-k sum by bisection on the float bit
+// pattern (values are probabilities >= 0, so the unsigned order is the numeric order): 31 counting passes find the k-th
+// largest value x_k; sum = sum(v > x_k) + (k - count(v > x_k)) * x_k; the gradient goes to the elements above x_k plus
+// the lowest-index ties (the oracle's tie rule).  No block-wide barrier is needed inside a problem.
 __device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scratch, float* s_red, int tid, int b,
                                                   int h, int heads, int bh, int n) {
-                float* col = scratch;                        // [n] values + [n] masked values
-        float* val = col + n;                        // n <= 4096 fits (32 KB)
-        float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
-        for (int i = tid; i < n * L.ext_ld; i += 128) dpx[i] = 0.f;
-        float loss_acc = 0.f;
-        const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
-        for (int t = t0; t < t1; ++t) {
-          const LossTerm T = L.terms[t];
-          const int tok = L.slot_tok[b * kMaxSlots + T.slot];
-          const float* src = L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
-          const uint8_t* mk = L.masks + (long long)T.mask * n;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = tid; i < n; i += 128) col[i] = __ldcg(src + i);
-          if (T.type == 0) {
-#pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-              const int k = side ? T.k_bg : T.k_fg;
-              const float w = side ? T.w_bg : T.w_fg;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              for (int i = tid; i < n; i += 128) val[i] = (mk[i] != 0) == (side == 0) ? col[i] : 0.f;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              float part = 0.f;
-              for (int i = tid; i < n; i += 128) {
-                const float vi = val[i];
-                int rank = 0;
-                for (int j = 0; j < n; ++j) {
-                  const float vj = val[j];
-                  rank += (vj > vi) || (vj == vi && j < i);
-                }
-                if (rank < k) {
-                  part += vi;
-                  const bool inside = (mk[i] != 0) == (side == 0);
-                  if (inside) dpx[(long long)i * L.ext_ld + tok] += (side ? w : -w) / (float)k * L.gscale;
-                }
-              }
-              const float tot = block128_sum(part, s_red, tid);
-              loss_acc += side ? w * tot / (float)k : w * (1.f - tot / (float)k);
-            }
-          } else {
-            const float* R = L.refs + ((long long)T.ref * heads + h) * n;
-            float sa = 0.f, sr = 0.f;
-            for (int i = tid; i < n; i += 128)
-              if (mk[i]) {
-                sa += col[i];
-                sr += R[i];
-              }
-            const float A = block128_sum(sa, s_red, tid) + L.eps;
-            const float Rs = block128_sum(sr, s_red, tid) + L.eps;
-            float l1 = 0.f, inner = 0.f;
-            for (int i = tid; i < n; i += 128)
-              if (mk[i]) {
-                const float ah = col[i] / A, rh = R[i] / Rs;
-                const float df = ah - rh;
-                const float sg = (df > 0.f) - (df < 0.f);
-                l1 += fabsf(df);
-                inner += sg * ah;
-              }
-            const float L1 = block128_sum(l1, s_red, tid);
-            const float In = block128_sum(inner, s_red, tid);
-            loss_acc += T.w_ref * L1;
-            for (int i = tid; i < n; i += 128)
-              if (mk[i]) {
-                const float ah = col[i] / A, rh = R[i] / Rs;
-                const float df = ah - rh;
-                const float sg = (df > 0.f) - (df < 0.f);
-                dpx[(long long)i * L.ext_ld + tok] += T.w_ref / A * (sg - In) * L.gscale;
-              }
-          }
+  const int warp = tid >> 5, lane = tid & 31;
+  float* val = scratch + warp * n;                       // this warp's working column
+  float* prob_loss = scratch + 4 * n;                    // [<= 160] per-problem loss contributions
+  float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
+  for (int i = tid; i < n * L.ext_ld; i += 128) dpx[i] = 0.f;
+  const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
+  // problem enumeration: energy term -> 2 consecutive ids (fg, bg), reference term -> 1 id
+  int n_prob = 0;
+  for (int t = t0; t < t1; ++t) n_prob += (L.terms[t].type == 0) ? 2 : 1;
+  __threadfence_block();
+  asm volatile("bar.sync 1, 128;" ::: "memory");         // dp_extra zero-fill complete before any accumulation
+  int pid = 0;
+  for (int t = t0; t < t1; ++t) {
+    const LossTerm T = L.terms[t];
+    const int nsub = (T.type == 0) ? 2 : 1;
+    for (int sub = 0; sub < nsub; ++sub, ++pid) {
+      if ((pid & 3) != warp) continue;
+      const int tok = L.slot_tok[b * kMaxSlots + T.slot];
+      const float* src = L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
+      const uint8_t* mk = L.masks + (long long)T.mask * n;
+      float contrib = 0.f;
+      if (T.type == 0) {
+        const int side = sub;                             // 0 = foreground (inside the mask), 1 = background
+        const int k = side ? T.k_bg : T.k_fg;
+        const float w = side ? T.w_bg : T.w_fg;
+        for (int i = lane; i < n; i += 32) val[i] = ((mk[i] != 0) == (side == 0)) ? __ldcg(src + i) : 0.f;
+        __syncwarp();
+        // bisection for the k-th largest bit pattern: invariant count(v >= lo) >= k, count(v >= hi) < k
+        uint32_t lo = 0u, hi = 0x7F800000u;
+        while (hi - lo > 1u) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          int c = 0;
+          for (int i = lane; i < n; i += 32) c += (__float_as_uint(val[i]) >= mid);
+          c = __reduce_add_sync(0xffffffffu, c);
+          if (c >= k) lo = mid; else hi = mid;
         }
-        if (tid == 0) L.loss_part[bh] = loss_acc;
+        const float xk = __uint_as_float(lo);
+        int c_gt = 0;
+        float s_gt = 0.f;
+        // lane-contiguous index blocks so that "lowest index first" among ties is a prefix over lanes
+        const int per = (n + 31) >> 5;
+        const int i0 = lane * per, i1 = min(n, i0 + per);
+        int ties_here = 0;
+        for (int i = i0; i < i1; ++i) {
+          const float v = val[i];
+          if (v > xk) { ++c_gt; s_gt += v; }
+          ties_here += (v == xk);
+        }
+        c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s_gt += __shfl_xor_sync(0xffffffffu, s_gt, o);
+        int excl = ties_here;                              // exclusive prefix of tie counts over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, excl, o);
+          if (lane >= o) excl += up;
+        }
+        excl -= ties_here;
+        const int need = k - c_gt;                         // ties to take (>= 1)
+        const float tot = s_gt + (float)need * xk;
+        contrib = side ? w * tot / (float)k : w * (1.f - tot / (float)k);
+        const float gval = (side ? w : -w) / (float)k * L.gscale;
+        int tr = excl;
+        for (int i = i0; i < i1; ++i) {
+          const float v = val[i];
+          bool sel = v > xk;
+          if (v == xk) { sel = tr < need; ++tr; }
+          if (sel && ((mk[i] != 0) == (side == 0))) atomicAdd(&dpx[(long long)i * L.ext_ld + tok], gval);
+        }
+      } else {
+        const float* R = L.refs + ((long long)T.ref * heads + h) * n;
+        float sa = 0.f, sr = 0.f;
+        for (int i = lane; i < n; i += 32) {
+          const float v = mk[i] ? __ldcg(src + i) : 0.f;
+          val[i] = v;
+          sa += v;
+          sr += mk[i] ? R[i] : 0.f;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        }
+        const float A = sa + L.eps, Rs = sr + L.eps;
+        float l1 = 0.f, inner = 0.f;
+        for (int i = lane; i < n; i += 32)
+          if (mk[i]) {
+            const float ah = val[i] / A, df = ah - R[i] / Rs;
+            const float sg = (df > 0.f) - (df < 0.f);
+            l1 += fabsf(df);
+            inner += sg * ah;
+          }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+          inner += __shfl_xor_sync(0xffffffffu, inner, o);
+        }
+        contrib = T.w_ref * l1;
+        for (int i = lane; i < n; i += 32)
+          if (mk[i]) {
+            const float df = val[i] / A - R[i] / Rs;
+            const float sg = (df > 0.f) - (df < 0.f);
+            atomicAdd(&dpx[(long long)i * L.ext_ld + tok], T.w_ref / A * (sg - inner) * L.gscale);
+          }
+      }
+      if (lane == 0 && pid < 160) prob_loss[pid] = contrib;
+      __syncwarp();
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (tid == 0) {                                          // fixed summation order => deterministic loss
+    float acc = 0.f;
+    for (int i = 0; i < n_prob && i < 160; ++i) acc += prob_loss[i];
+    L.loss_part[bh] = acc;
+  }
+  (void)s_red;
 }
 
 template <int DPB, int D16>

@@ -53,8 +53,8 @@ def gemm(M, N, K, name):
     x = torch.randn(M, K, device=dev).half()
     w = torch.randn(N, K, device=dev).half()
     res = torch.randn(M, N, device=dev).half()
-    for v2 in (0, 1):
-        lib().b200lmd_set_option(b"gemm_v2", ctypes.c_int(v2))
+    for v2 in (1, 3):
+        lib().b200lmd_set_option(b"gemm_v3", ctypes.c_int(int(v2 == 3)))
         ms = timeit(lambda: ops.linear(x, w, None, res))
         byts = 2.0 * (M * K + 2 * M * N + N * K)
         print(f"{name} v2={v2}: M={M} N={N} K={K}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s  "
@@ -76,8 +76,8 @@ def geglu(M, F, K):
 def conv(B, H, C_in, C_out):
     x = torch.randn(B, H, H, C_in, device=dev).half()
     w = torch.randn(C_out, 9, C_in, device=dev).half()
-    for v2 in (0, 1):
-        lib().b200lmd_set_option(b"gemm_v2", ctypes.c_int(v2))
+    for v2 in (1, 3):
+        lib().b200lmd_set_option(b"gemm_v3", ctypes.c_int(int(v2 == 3)))
         ms = timeit(lambda: ops.conv3x3(x, w))
         print(f"conv3x3 v2={v2} B={B} {H}x{H} {C_in}->{C_out}: {ms * 1e3:.1f} us  "
               f"{2.0 * B * H * H * C_out * 9 * C_in / ms / 1e9:.1f} TFLOP/s")
