@@ -135,7 +135,7 @@ def xattn_roofline(dev, with_loss=True):
     graph = torch.cuda.CUDAGraph()          # device time only: the three launches replayed back to back
     with torch.cuda.graph(graph):
         op()
-    reps, tot = 20, 0.0
+    reps, times = 20, []
     for _ in range(reps):
         flush.zero_()                       # L2 flush (256 MB > 126 MB L2) between timed iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -143,8 +143,10 @@ def xattn_roofline(dev, with_loss=True):
         graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    ms = tot / reps
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / reps
+    if os.environ.get("B200_BENCH_VERBOSE"):
+        print("xattn reps (ms):", [round(t, 4) for t in times], file=sys.stderr)
     flops = B * (2 * n * C * C * 2 + 2 * n * T * C * 2)
     peak, _, how = peaks()
     ach = flops / (ms * 1e-3) / 1e12

@@ -193,6 +193,9 @@ int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void* k_slab, c
                             const b200lmd_xattn_loss* loss, int B, int n, int heads, int head_dim, int nk, int k_alloc,
                             float scale, void* stream);
 
+/* profiling aid: device buffer [grid][8] of %globaltimer stamps written by the fused kernel (NULL disables) */
+int b200lmd_set_debug_buffer(void* p);
+
 /* ------------------------------------------------------------------------------------------------ normalisation
  * GroupNorm (+ optional SiLU) over NHWC fp16 x[B, n, C]: stats then apply (torch.nn.GroupNorm inside diffusers
  * ResnetBlock2D and models/transformer_2d.py:146,283).  sums: fp32 [B, groups, 2] scratch (zeroed by the call). */

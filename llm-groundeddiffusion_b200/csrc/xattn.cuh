@@ -77,7 +77,7 @@ __device__ __forceinline__ float block128_sum(float v, float* red, int tid) {
 
 
 // Loss / gradient of one (image, head) from the published P columns (utils/guidance.py:91-242).  Called by the 128
-// softmax threads (4 warps) of the last CTA of that (image, head); scratch: >= 4*n + 160 floats of shared memory (n <= 1536 with the callers' buffers).
+// softmax threads (4 warps) of the last CTA of that (image, head); scratch: >= 24*n + 640 bytes of shared memory (n <= 1024 with the callers' buffers).
 //
 // Work is split into independent "problems", one warp each (round-robin): an energy term contributes two top-k
 // selections (foreground / background), a reference term one normalised-L1.  Top-k sum by bisection on the float bit
@@ -89,6 +89,7 @@ __device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scr
   const int warp = tid >> 5, lane = tid & 31;
   float* val = scratch + warp * n;                       // this warp's working column
   float* prob_loss = scratch + 4 * n;                    // [<= 160] per-problem loss contributions
+  unsigned short* hb = reinterpret_cast<unsigned short*>(prob_loss + 160) + warp * n;   // fp16 bit patterns
   float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
   for (int i = tid; i < n * L.ext_ld; i += 128) dpx[i] = 0.f;
   const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
@@ -111,18 +112,23 @@ __device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scr
         const int side = sub;                             // 0 = foreground (inside the mask), 1 = background
         const int k = side ? T.k_bg : T.k_fg;
         const float w = side ? T.w_bg : T.w_fg;
-        for (int i = lane; i < n; i += 32) val[i] = ((mk[i] != 0) == (side == 0)) ? __ldcg(src + i) : 0.f;
+        for (int i = lane; i < n; i += 32) {
+          const float v = ((mk[i] != 0) == (side == 0)) ? __ldcg(src + i) : 0.f;
+          val[i] = v;
+          hb[i] = __half_as_ushort(__float2half_rn(v));     // the maps are fp16 values: the bit pattern is exact
+        }
         __syncwarp();
-        // bisection for the k-th largest bit pattern: invariant count(v >= lo) >= k, count(v >= hi) < k
-        uint32_t lo = 0u, hi = 0x7F800000u;
+        // bisection for the k-th largest fp16 bit pattern (non-negative values: unsigned order == numeric order):
+        // invariant count(v >= lo) >= k, count(v >= hi) < k; 15 counting passes
+        uint32_t lo = 0u, hi = 0x7C00u;
         while (hi - lo > 1u) {
           const uint32_t mid = lo + ((hi - lo) >> 1);
           int c = 0;
-          for (int i = lane; i < n; i += 32) c += (__float_as_uint(val[i]) >= mid);
+          for (int i = lane; i < n; i += 32) c += ((uint32_t)hb[i] >= mid);
           c = __reduce_add_sync(0xffffffffu, c);
           if (c >= k) lo = mid; else hi = mid;
         }
-        const float xk = __uint_as_float(lo);
+        const float xk = __half2float(__ushort_as_half((unsigned short)lo));
         int c_gt = 0;
         float s_gt = 0.f;
         // lane-contiguous index blocks so that "lowest index first" among ties is a prefix over lanes

@@ -2,7 +2,8 @@
 //
 //   out[rows, :] = residual + bias_o + softmax(scale * (x Wq^T) K^T) V  Wo^T        (+ loss, d loss/dP, optional maps)
 //
-// Grid = clusters of 8 CTAs; a cluster owns one 128-row tile of x (rows of ONE image: n % 128 == 0), CTA rank = head.
+// Grid = clusters of 4 CTAs (4 heads); two clusters share one 128-row tile of x (rows of ONE image: n % 128 == 0).
+// (Clusters of 8 do not all fit on the GPU at once - 16 were needed, the profile showed a second wave - clusters of 4 do.)
 //   phase 1  Q_h   = x_tile . Wq_h^T        tcgen05 128 x d x C GEMM; the x tile is fetched ONCE per cluster: each CTA
 //                                           TMA-loads a 16-row slice of every k-block and multicasts it to all 8 CTAs
 //   core     S = Q_h K_h^T -> softmax (one thread per row, from TMEM) -> P (fp16 smem) -> O_h = P V_h
@@ -31,7 +32,16 @@ struct FusedXattnParams {
   __half* probs_tok;        // [B*8, n]
   int has_loss;
   XattnLoss L;
+  int* tile_flags;           // [row tiles] zero on entry: counts the heads of a row tile whose O_h is published
+  unsigned long long* dbg;   // optional [grid][8] %globaltimer stamps (phase timeline), null in production
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FUSED_STAMP(i) do { if (p.dbg && threadIdx.x == 64) p.dbg[(long long)blockIdx.x * 8 + (i)] = gtimer(); } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -73,12 +83,13 @@ struct FusedCfg {
   static constexpr int P_BYTES = 2 * 16384;                 // aliases the stage ring
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(Q_BYTES + P_BYTES <= RING_BYTES, "core scratch must fit in the stage ring");
+  static_assert(128 * (D + 8) * 2 <= RING_BYTES, "epilogue staging must fit in the stage ring");
   static constexpr int SMEM_BYTES = RING_BYTES + K_BYTES + V_BYTES + 1024 + 512;
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
 template <int D>
-__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(192, 1)
 xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVt,
                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWo,
@@ -104,7 +115,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float* s_red = reinterpret_cast<float*>(s_flag + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int h = (int)cluster_ctarank();            // head
+  const int cr = (int)cluster_ctarank();           // rank inside the 4-CTA cluster
+  const int h = (int)(blockIdx.x & 7);             // head (clusters 2rt and 2rt+1 hold heads 0-3 and 4-7)
   const int rt = blockIdx.x >> 3;                  // row tile
   const int row0 = rt * 128;
   const int b = row0 / p.n;                        // image of this tile
@@ -120,7 +132,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (elect_one()) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 8);
+        mbar_init(&empty_bar[s], 4);
       }
       mbar_init(kv_full, 1);
       mbar_init(acc_full, 1);
@@ -136,6 +148,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   cluster_sync_all();           // every CTA's barriers exist before anyone multicasts into / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  FUSED_STAMP(0);
   const uint32_t tAcc = tmem_base;          // Q_h, then O_h, then the output tile (D columns)
   const uint32_t tS = tmem_base + 256;      // scores (80 columns)
 
@@ -152,7 +165,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-        tma_load_2d_mcast(sa + h * 2048, &tmX, &full_bar[stage], kb * 64, row0 + h * 16, (uint16_t)0xFF);
+        tma_load_2d_mcast(sa + cr * 4096, &tmX, &full_bar[stage], kb * 64, row0 + cr * 32, (uint16_t)0xF);
         tma_load_2d(sa + Cfg::A_BYTES, &tmWq, &full_bar[stage], kb * 64, h * D);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -173,7 +186,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint64_t bd = make_desc_k_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(tAcc, ad + k * 2, bd + k * 2, idesc_g, (kb | k) ? 1u : 0u);
-        tc_commit_mcast(&empty_bar[stage], (uint16_t)0xFF);
+        tc_commit_mcast(&empty_bar[stage], (uint16_t)0xF);
         if (kb == nkb - 1) tc_commit(acc_full);
       }
       __syncwarp();
@@ -226,6 +239,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // ---- Q_h: TMEM -> fp16 -> smem A operand (and the optional Q slab for the backward)
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    FUSED_STAMP(1);
     __half* qrow = p.q_slab ? p.q_slab + ((long long)bh * p.n + tok) * (Cfg::DPB * 64) : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < Cfg::DPB * 64; c0 += 16) {
@@ -257,6 +271,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // ---- softmax over the 77 keys
     mbar_wait(acc_full, 1);
     tc_fence_after();
+    FUSED_STAMP(2);
     float m = -INFINITY;
 #pragma unroll 1
     for (int c0 = 0; c0 < 80; c0 += 16) {
@@ -327,7 +342,12 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // ---- O_h: TMEM -> fp16 -> o_buf[rows, h*D ...]  (the A operand of phase 2, read back through L2)
     mbar_wait(acc_full, 0);   // third completion of acc_full: parity 0 again
     tc_fence_after();
-    __half* orow = p.o_buf + grow * p.C + h * D;
+    FUSED_STAMP(3);
+    // stage the row in shared memory (ring scratch: Q / P are dead once P.V has completed), then leave as full row
+    // segments: consecutive lanes write consecutive 16-byte pieces of a row
+    constexpr int OLD = D + 8;                         // padded row stride (halves)
+    __half* stgO = reinterpret_cast<__half*>(ring);
+    const uint32_t stgO_s = smem_u32(stgO);
 #pragma unroll 1
     for (int c0 = 0; c0 < D; c0 += 16) {
       uint32_t v[16];
@@ -338,18 +358,41 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       s0.z = pack_h2(__uint_as_float(v[4]), __uint_as_float(v[5])); s0.w = pack_h2(__uint_as_float(v[6]), __uint_as_float(v[7]));
       s1.x = pack_h2(__uint_as_float(v[8]), __uint_as_float(v[9])); s1.y = pack_h2(__uint_as_float(v[10]), __uint_as_float(v[11]));
       s1.z = pack_h2(__uint_as_float(v[12]), __uint_as_float(v[13])); s1.w = pack_h2(__uint_as_float(v[14]), __uint_as_float(v[15]));
-      *reinterpret_cast<uint4*>(orow + c0) = s0;
-      *reinterpret_cast<uint4*>(orow + c0 + 8) = s1;
+      sts128(stgO_s + (r * OLD + c0) * 2, s0);
+      sts128(stgO_s + (r * OLD + c0 + 8) * 2, s1);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    {
+      constexpr int PPR = D / 8;                       // 16-byte pieces per row
+      for (int pi = tid; pi < 128 * PPR; pi += 128) {
+        const int row = pi / PPR, pc = pi - row * PPR;
+        *reinterpret_cast<uint4*>(p.o_buf + ((long long)row0 + row) * p.C + h * D + pc * 8) =
+            lds128(stgO_s + (row * OLD + pc * 8) * 2);
+      }
     }
     if (p.lse2) p.lse2[(long long)bh * p.n + tok] = row_m + log2f(row_l);
     __threadfence();
     fence_proxy_async_all();
     tc_fence_before();
+    // publish: this head's O_h is in L2; phase 2 needs all 8 heads of the row tile (two clusters)
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+      atomicAdd(&p.tile_flags[rt], 1);
+      uint32_t spins = 0;
+      while (atomicAdd(&p.tile_flags[rt], 0) < 8) {
+        if (++spins > B200_SPIN_LIMIT) __trap();
+        __nanosleep(64);
+      }
+      __threadfence();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
   }
-  // every CTA has published O_h and is done with the ring scratch
+  // every CTA of the cluster has left the core (ring scratch free) and all 8 O_h of the row tile are visible
   __syncwarp();
+  FUSED_STAMP(4);
   cluster_sync_all();
   tc_fence_after();
+  FUSED_STAMP(5);
 
   // ------------------------------------------------------------------ phase 2: out slice = O_tile . Wo_h^T
   if (warp == 0) {
@@ -361,7 +404,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-        tma_load_2d_mcast(sa + h * 2048, &tmO, &full_bar[stage], kb * 64, row0 + h * 16, (uint16_t)0xFF);
+        tma_load_2d_mcast(sa + cr * 4096, &tmO, &full_bar[stage], kb * 64, row0 + cr * 32, (uint16_t)0xF);
         tma_load_2d(sa + Cfg::A_BYTES, &tmWo, &full_bar[stage], kb * 64, h * D);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -378,7 +421,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint64_t bd = make_desc_k_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(tAcc, ad + k * 2, bd + k * 2, idesc_g, (kb | k) ? 1u : 0u);
-        tc_commit_mcast(&empty_bar[stage], (uint16_t)0xFF);
+        tc_commit_mcast(&empty_bar[stage], (uint16_t)0xF);
         if (kb == nkb - 1) tc_commit(acc_full);
       }
       __syncwarp();
@@ -387,8 +430,19 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else {
     mbar_wait(acc_full, 1);   // fourth completion
     tc_fence_after();
-    const __half* rrow = p.residual ? p.residual + grow * p.C + h * D : nullptr;
-    __half* orow = p.out + grow * p.C + h * D;
+    FUSED_STAMP(6);
+    constexpr int OLD = D + 8;
+    constexpr int PPR = D / 8;
+    __half* stgE = reinterpret_cast<__half*>(ring);   // no peer writes into this CTA's ring after its last phase-2 MMA
+    const uint32_t stgE_s = smem_u32(stgE);
+    if (p.residual) {                                   // residual tile -> staging, full row segments
+      for (int pi = tid; pi < 128 * PPR; pi += 128) {
+        const int row = pi / PPR, pc = pi - row * PPR;
+        sts128(stgE_s + (row * OLD + pc * 8) * 2,
+               *reinterpret_cast<const uint4*>(p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < D; c0 += 16) {
       uint32_t v[16];
@@ -397,8 +451,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       float f[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + (p.bias_o ? __ldg(p.bias_o + h * D + c0 + i) : 0.f);
-      if (rrow) {
-        uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + 8);
+      if (p.residual) {
+        const uint4 r0 = lds128(stgE_s + (r * OLD + c0) * 2), r1 = lds128(stgE_s + (r * OLD + c0 + 8) * 2);
         const __half2* a = reinterpret_cast<const __half2*>(&r0);
         const __half2* c = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
@@ -408,11 +462,16 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           f[8 + 2 * i] += t1.x; f[8 + 2 * i + 1] += t1.y;
         }
       }
-      uint4 s0, s1;
-      s0.x = pack_h2(f[0], f[1]); s0.y = pack_h2(f[2], f[3]); s0.z = pack_h2(f[4], f[5]); s0.w = pack_h2(f[6], f[7]);
-      s1.x = pack_h2(f[8], f[9]); s1.y = pack_h2(f[10], f[11]); s1.z = pack_h2(f[12], f[13]); s1.w = pack_h2(f[14], f[15]);
-      *reinterpret_cast<uint4*>(orow + c0) = s0;
-      *reinterpret_cast<uint4*>(orow + c0 + 8) = s1;
+      sts128(stgE_s + (r * OLD + c0) * 2,
+             make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])));
+      sts128(stgE_s + (r * OLD + c0 + 8) * 2,
+             make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15])));
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int pi = tid; pi < 128 * PPR; pi += 128) {
+      const int row = pi / PPR, pc = pi - row * PPR;
+      *reinterpret_cast<uint4*>(p.out + ((long long)row0 + row) * p.C + h * D + pc * 8) =
+          lds128(stgE_s + (row * OLD + pc * 8) * 2);
     }
     tc_fence_before();
 
@@ -432,6 +491,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
   }
+  FUSED_STAMP(7);
   __syncthreads();
   cluster_sync_all();   // nobody exits while a peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
