@@ -18,7 +18,7 @@ inline XattnLaunch build_xattn(const __half* q, const __half* k, const __half* v
   XattnLaunch L;
   memset(&L, 0, sizeof(L));
   if (nk > 128) throw std::runtime_error("xattn: at most 128 keys");
-  if (loss && nq > 1024) throw std::runtime_error("xattn loss: at most 1024 query tokens per image");
+  if (loss && nq > 1200) throw std::runtime_error("xattn loss: at most 1200 query tokens per image");
   const int dp = round_dp(d), d16 = round_d16(d), BH = B * heads;
   L.dpb = dp / 64; L.d16 = d16;
   L.tmQ = slab_rm_map(q, BH, nq_alloc, dp, 128);
@@ -131,7 +131,10 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     using namespace b200;
     if (!b200lmd_xattn_fused_supported(heads, head_dim, n)) throw std::runtime_error("xattn_fused: unsupported shape");
     if (nk > 80 || k_alloc < 80) throw std::runtime_error("xattn_fused: needs <= 80 text keys in 80-row slabs");
-    if (loss && n > 1024) throw std::runtime_error("xattn loss: at most 1024 query tokens per image");
+    {
+      const int kv_bytes = head_dim == 64 ? 26624 : (head_dim == 80 ? 40960 : 71680);   // FusedCfg K_BYTES + V_BYTES
+      if (loss && n > (kv_bytes - 3520) / 24) throw std::runtime_error("xattn_fused loss: too many query tokens per image");
+    }
     const int C = heads * head_dim;
     const long long M = (long long)B * n;
     const int dp = round_dp(head_dim), d16 = round_d16(head_dim);

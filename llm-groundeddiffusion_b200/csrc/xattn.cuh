@@ -17,6 +17,7 @@
 namespace b200 {
 
 static constexpr int kMaxSlots = 48;
+static constexpr int kMaxTerms = 80;     // loss terms per image (48 token slots + reference terms)
 
 struct LossTerm {
   int type;     // 0 = energy (fg/bg top-k), 1 = reference-attention L1
@@ -77,7 +78,7 @@ __device__ __forceinline__ float block128_sum(float v, float* red, int tid) {
 
 
 // Loss / gradient of one (image, head) from the published P columns (utils/guidance.py:91-242).  Called by the 128
-// softmax threads (4 warps) of the last CTA of that (image, head); scratch: >= 24*n + 640 bytes of shared memory (n <= 1024 with the callers' buffers).
+// softmax threads (4 warps) of the last CTA of that (image, head); scratch: >= 24*n + 640 + 36*kMaxTerms bytes of shared memory (n <= 900 with the callers' buffers).
 //
 // Work is split into independent "problems", one warp each (round-robin): an energy term contributes two top-k
 // selections (foreground / background), a reference term one normalised-L1.  Top-k sum by bisection on the float bit
@@ -93,14 +94,24 @@ __device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scr
   float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
   for (int i = tid; i < n * L.ext_ld; i += 128) dpx[i] = 0.f;
   const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
+  // the term table of this image goes to shared memory once (each global read is a full memory round trip; walking
+  // the table from global memory in every warp dominated the reduction)
+  LossTerm* sterms = reinterpret_cast<LossTerm*>(hb + (4 - warp) * n);   // behind the four fp16 columns
+  {
+    const int* src = reinterpret_cast<const int*>(L.terms + t0);
+    int* dst = reinterpret_cast<int*>(sterms);
+    const int words = min(t1 - t0, kMaxTerms) * (int)(sizeof(LossTerm) / 4);
+    for (int i = tid; i < words; i += 128) dst[i] = src[i];
+  }
+  __threadfence_block();
+  asm volatile("bar.sync 1, 128;" ::: "memory");         // table staged, dp_extra zero-fill complete
+  const int nterms = min(t1 - t0, kMaxTerms);
   // problem enumeration: energy term -> 2 consecutive ids (fg, bg), reference term -> 1 id
   int n_prob = 0;
-  for (int t = t0; t < t1; ++t) n_prob += (L.terms[t].type == 0) ? 2 : 1;
-  __threadfence_block();
-  asm volatile("bar.sync 1, 128;" ::: "memory");         // dp_extra zero-fill complete before any accumulation
+  for (int t = 0; t < nterms; ++t) n_prob += (sterms[t].type == 0) ? 2 : 1;
   int pid = 0;
-  for (int t = t0; t < t1; ++t) {
-    const LossTerm T = L.terms[t];
+  for (int t = 0; t < nterms; ++t) {
+    const LossTerm T = sterms[t];
     const int nsub = (T.type == 0) ? 2 : 1;
     for (int sub = 0; sub < nsub; ++sub, ++pid) {
       if ((pid & 3) != warp) continue;

@@ -371,12 +371,13 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
     if (p.lse2) p.lse2[(long long)bh * p.n + tok] = row_m + log2f(row_l);
-    __threadfence();
     fence_proxy_async_all();
     tc_fence_before();
-    // publish: this head's O_h is in L2; phase 2 needs all 8 heads of the row tile (two clusters)
+    // publish: this head's O_h is in L2; phase 2 needs all 8 heads of the row tile (two clusters).  The CTA barrier
+    // orders every thread's stores before thread 0's gpu-scope fence (fences are cumulative), then the flag goes up.
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid == 0) {
+      __threadfence();
       atomicAdd(&p.tile_flags[rt], 1);
       uint32_t spins = 0;
       while (atomicAdd(&p.tile_flags[rt], 0) < 8) {
@@ -428,21 +429,37 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
-    mbar_wait(acc_full, 1);   // fourth completion
-    tc_fence_after();
-    FUSED_STAMP(6);
     constexpr int OLD = D + 8;
     constexpr int PPR = D / 8;
-    __half* stgE = reinterpret_cast<__half*>(ring);   // no peer writes into this CTA's ring after its last phase-2 MMA
+    // residual tile -> shared memory WHILE phase 2 runs on the tensor core (these warps are idle until the accumulator
+    // is complete).  It lands in the K/V region, dead since the core; loads are batched so they overlap each other.
+    __half* stgE = reinterpret_cast<__half*>(sK);
     const uint32_t stgE_s = smem_u32(stgE);
-    if (p.residual) {                                   // residual tile -> staging, full row segments
-      for (int pi = tid; pi < 128 * PPR; pi += 128) {
-        const int row = pi / PPR, pc = pi - row * PPR;
-        sts128(stgE_s + (row * OLD + pc * 8) * 2,
-               *reinterpret_cast<const uint4*>(p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8));
+    static_assert(128 * (D + 8) * 2 <= Cfg::K_BYTES + Cfg::V_BYTES, "residual staging must fit in the K/V region");
+    if (p.residual) {
+      constexpr int NP = 128 * PPR / 128;              // pieces per thread
+#pragma unroll 1
+      for (int j0 = 0; j0 < NP; j0 += 5) {
+        uint4 tmp[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int pi = tid + (j0 + j) * 128;
+          const int row = pi / PPR, pc = pi - row * PPR;
+          tmp[j] = (j0 + j < NP) ? *reinterpret_cast<const uint4*>(p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8)
+                                 : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int pi = tid + (j0 + j) * 128;
+          const int row = pi / PPR, pc = pi - row * PPR;
+          if (j0 + j < NP) sts128(stgE_s + (row * OLD + pc * 8) * 2, tmp[j]);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    mbar_wait(acc_full, 1);   // fourth completion
+    tc_fence_after();
+    FUSED_STAMP(6);
 #pragma unroll 1
     for (int c0 = 0; c0 < D; c0 += 16) {
       uint32_t v[16];

@@ -131,6 +131,8 @@ def build_key_tables(samples: Sequence[SampleLayout], slot_of, key, n, heads, n_
                     refs.append(s.ref_maps[o][bi])       # resolved per step in KeyLoss.set_step
                     for tok in toks:
                         terms.append((1, slot_of[b][tok], mid, 0, 0, 0.0, 0.0, w, rid))
+        if len(terms) - term_off[-1] > 80:
+            raise ValueError(f"image {b}: more than 80 loss terms")
         term_off.append(len(terms))
     terms_np = np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, dtype=TERM_DTYPE)
     masks_np = np.stack(masks) if masks else np.zeros((1, n), dtype=np.uint8)
