@@ -94,7 +94,7 @@ XATTN_DRAM_BYTES_NCU = None
 def xattn_roofline(dev, with_loss=True):
     """the fused cross-attention+loss kernel at the config's guidance shape (B=8, n=256, C=1280, heads 8, T=77):
     algorithmic FLOPs 2nC^2 (to_q) + 2nTC (QK^T) + 2nTC (PV) + 2nC^2 (to_out) per sample, one
-    launch, timed with CUDA events around a graph replay of that single kernel, L2 flushed between repetitions."""
+    launch, timed with CUDA events on the launching stream, L2 flushed between repetitions."""
     from lgd_b200 import guidance as G, ops
     B, heads, d, n, T, ctx = 8, 8, 160, 256, 77, 768
     C = heads * d
@@ -123,7 +123,7 @@ def xattn_roofline(dev, with_loss=True):
     params = G.LossParams(loss_scale=5.0, fg_weight=1.0, bg_weight=4.0)
     st, so = G.assign_slots(lay, params)
     kl = G.KeyLoss(lay, torch.from_numpy(st).to(dev), so, ("up", 1, 0, 0), n, heads, 4, params, dev, gscale=256.0)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush = torch.empty(1024 * 1024 * 1024, dtype=torch.uint8, device=dev)
     res = x.clone()
 
     def op():      # ONE launch: xattn_fused_kernel (to_q, QK^T, softmax, loss + dP, PV, to_out + bias + residual)
@@ -132,15 +132,15 @@ def xattn_roofline(dev, with_loss=True):
     for _ in range(3):
         op()
     torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()          # device time only: the three launches replayed back to back
-    with torch.cuda.graph(graph):
-        op()
+    # device time of the launch: the L2 flush (1 GiB memset, > 126 MB L2, ~300 us) is still running while the host
+    # enqueues event / launch / event behind it, so the events bracket the kernel (and the few-byte flag memset the
+    # launcher issues in front of it) with no host launch latency in between
     reps, times = 20, []
     for _ in range(reps):
-        flush.zero_()                       # L2 flush (256 MB > 126 MB L2) between timed iterations
+        flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        graph.replay()
+        op()
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))

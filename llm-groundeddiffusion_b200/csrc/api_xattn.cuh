@@ -18,7 +18,7 @@ inline XattnLaunch build_xattn(const __half* q, const __half* k, const __half* v
   XattnLaunch L;
   memset(&L, 0, sizeof(L));
   if (nk > 128) throw std::runtime_error("xattn: at most 128 keys");
-  if (loss && nq > 1200) throw std::runtime_error("xattn loss: at most 1200 query tokens per image");
+  if (loss && nq > 1280) throw std::runtime_error("xattn loss: at most 1280 query tokens per image");
   const int dp = round_dp(d), d16 = round_d16(d), BH = B * heads;
   L.dpb = dp / 64; L.d16 = d16;
   L.tmQ = slab_rm_map(q, BH, nq_alloc, dp, 128);
@@ -84,15 +84,26 @@ inline unsigned long long*& fused_dbg() {
   return p;
 }
 // zeroed per launch (stream-ordered memset, graph-capturable); grown on demand outside of capture
-inline int* fused_flags(int n_tiles, cudaStream_t st) {
+inline int* fused_flags(int n_ints, cudaStream_t st) {
   static int* buf = nullptr;
   static int cap = 0;
-  if (n_tiles > cap) {
+  if (n_ints > cap) {
     if (buf) cudaFree(buf);
-    cap = n_tiles < 4096 ? 4096 : n_tiles;
+    cap = n_ints < 8192 ? 8192 : n_ints;
     B200_CHECK(cudaMalloc(&buf, sizeof(int) * cap));
   }
-  B200_CHECK(cudaMemsetAsync(buf, 0, sizeof(int) * n_tiles, st));
+  B200_CHECK(cudaMemsetAsync(buf, 0, sizeof(int) * n_ints, st));
+  return buf;
+}
+// per (image, head, row tile) loss partials; never needs zeroing
+inline float* fused_partials(int n) {
+  static float* buf = nullptr;
+  static int cap = 0;
+  if (n > cap) {
+    if (buf) cudaFree(buf);
+    cap = n < 32768 ? 32768 : n;
+    B200_CHECK(cudaMalloc(&buf, sizeof(float) * cap));
+  }
   return buf;
 }
 inline CUtensorMap rowmajor_map_2d(const __half* p, long long rows, int cols, int ld, int box_rows) {
@@ -132,8 +143,7 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     if (!b200lmd_xattn_fused_supported(heads, head_dim, n)) throw std::runtime_error("xattn_fused: unsupported shape");
     if (nk > 80 || k_alloc < 80) throw std::runtime_error("xattn_fused: needs <= 80 text keys in 80-row slabs");
     {
-      const int kv_bytes = head_dim == 64 ? 26624 : (head_dim == 80 ? 40960 : 71680);   // FusedCfg K_BYTES + V_BYTES
-      if (loss && n > (kv_bytes - 3520) / 24) throw std::runtime_error("xattn_fused loss: too many query tokens per image");
+      if (loss && n > 1280) throw std::runtime_error("xattn_fused loss: at most 1280 query tokens per image");
     }
     const int C = heads * head_dim;
     const long long M = (long long)B * n;
@@ -150,7 +160,11 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     if (loss) p.L = *reinterpret_cast<const XattnLoss*>(loss);
     p.dbg = fused_dbg();
     // per-row-tile arrival counters live right behind the scratch rows of o_scratch's owner: a small static buffer
-    p.tile_flags = fused_flags((int)(M / 128), (cudaStream_t)stream);
+    const int n_tiles = (int)(M / 128);
+    p.tile_flags = fused_flags(n_tiles + 2 * B * 8, (cudaStream_t)stream);
+    p.bh_ready = p.tile_flags + n_tiles;
+    p.bh_done = p.bh_ready + B * 8;
+    p.loss_partials = fused_partials(n_tiles * 8);
     CUtensorMap tmX = rowmajor_map_2d((const __half*)x, M, C, C, 32);
     CUtensorMap tmO = rowmajor_map_2d((const __half*)o_scratch, M, C, C, 32);
     CUtensorMap tmWq = rowmajor_map_2d((const __half*)wq, C, C, C, head_dim);

@@ -85,139 +85,312 @@ __device__ __forceinline__ float block128_sum(float v, float* red, int tid) {
 // pattern (values are probabilities >= 0, so the unsigned order is the numeric order): 31 counting passes find the k-th
 // largest value x_k; sum = sum(v > x_k) + (k - count(v > x_k)) * x_k; the gradient goes to the elements above x_k plus
 // the lowest-index ties (the oracle's tie rule).  No block-wide barrier is needed inside a problem.
-__device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scratch, float* s_red, int tid, int b,
-                                                  int h, int heads, int bh, int n) {
-  const int warp = tid >> 5, lane = tid & 31;
-  float* val = scratch + warp * n;                       // this warp's working column
-  float* prob_loss = scratch + 4 * n;                    // [<= 160] per-problem loss contributions
-  unsigned short* hb = reinterpret_cast<unsigned short*>(prob_loss + 160) + warp * n;   // fp16 bit patterns
-  float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
-  for (int i = tid; i < n * L.ext_ld; i += 128) dpx[i] = 0.f;
-  const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
-  // the term table of this image goes to shared memory once (each global read is a full memory round trip; walking
-  // the table from global memory in every warp dominated the reduction)
-  LossTerm* sterms = reinterpret_cast<LossTerm*>(hb + (4 - warp) * n);   // behind the four fp16 columns
-  {
-    const int* src = reinterpret_cast<const int*>(L.terms + t0);
-    int* dst = reinterpret_cast<int*>(sterms);
-    const int words = min(t1 - t0, kMaxTerms) * (int)(sizeof(LossTerm) / 4);
-    for (int i = tid; i < words; i += 128) dst[i] = src[i];
-  }
-  __threadfence_block();
-  asm volatile("bar.sync 1, 128;" ::: "memory");         // table staged, dp_extra zero-fill complete
-  const int nterms = min(t1 - t0, kMaxTerms);
-  // problem enumeration: energy term -> 2 consecutive ids (fg, bg), reference term -> 1 id
-  int n_prob = 0;
-  for (int t = 0; t < nterms; ++t) n_prob += (sterms[t].type == 0) ? 2 : 1;
-  int pid = 0;
-  for (int t = 0; t < nterms; ++t) {
-    const LossTerm T = sterms[t];
-    const int nsub = (T.type == 0) ? 2 : 1;
-    for (int sub = 0; sub < nsub; ++sub, ++pid) {
-      if ((pid & 3) != warp) continue;
-      const int tok = L.slot_tok[b * kMaxSlots + T.slot];
-      const float* src = L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
-      const uint8_t* mk = L.masks + (long long)T.mask * n;
-      float contrib = 0.f;
-      if (T.type == 0) {
-        const int side = sub;                             // 0 = foreground (inside the mask), 1 = background
-        const int k = side ? T.k_bg : T.k_fg;
-        const float w = side ? T.w_bg : T.w_fg;
-        for (int i = lane; i < n; i += 32) {
-          const float v = ((mk[i] != 0) == (side == 0)) ? __ldcg(src + i) : 0.f;
-          val[i] = v;
-          hb[i] = __half_as_ushort(__float2half_rn(v));     // the maps are fp16 values: the bit pattern is exact
-        }
-        __syncwarp();
-        // bisection for the k-th largest fp16 bit pattern (non-negative values: unsigned order == numeric order):
-        // invariant count(v >= lo) >= k, count(v >= hi) < k; 15 counting passes
-        uint32_t lo = 0u, hi = 0x7C00u;
-        while (hi - lo > 1u) {
-          const uint32_t mid = lo + ((hi - lo) >> 1);
-          int c = 0;
-          for (int i = lane; i < n; i += 32) c += ((uint32_t)hb[i] >= mid);
-          c = __reduce_add_sync(0xffffffffu, c);
-          if (c >= k) lo = mid; else hi = mid;
-        }
-        const float xk = __half2float(__ushort_as_half((unsigned short)lo));
-        int c_gt = 0;
-        float s_gt = 0.f;
-        // lane-contiguous index blocks so that "lowest index first" among ties is a prefix over lanes
-        const int per = (n + 31) >> 5;
-        const int i0 = lane * per, i1 = min(n, i0 + per);
-        int ties_here = 0;
-        for (int i = i0; i < i1; ++i) {
-          const float v = val[i];
-          if (v > xk) { ++c_gt; s_gt += v; }
-          ties_here += (v == xk);
-        }
-        c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+// ---- loss reduction: one warp per problem ((phrase, side) energy or one reference-attention term) with the whole map
+// column in registers.  Lane L owns the contiguous index block [L*per, L*per+per) so that "lowest index first" among
+// ties is a prefix over lanes.
+template <int PERMAX>
+struct LossRaw {
+  float v[PERMAX];     // P column values (fp16-representable)
+  float r[PERMAX];     // reference map values (reference terms only)
+  uint64_t m;          // bit j: mask byte of element j is non-zero
+};
+
+struct LossProb {      // decoded problem
+  const float* src;
+  const uint8_t* mk;
+  const float* R;      // nullptr for energy problems
+  int tok, side, k;
+  float w;
+};
+
+template <int PERMAX>
+__device__ __forceinline__ void loss_load(LossRaw<PERMAX>& q, const LossProb& P, int n, int per, int lane) {
+  const int i0 = lane * per;
+  q.m = 0ull;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) s_gt += __shfl_xor_sync(0xffffffffu, s_gt, o);
-        int excl = ties_here;                              // exclusive prefix of tie counts over lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, excl, o);
-          if (lane >= o) excl += up;
-        }
-        excl -= ties_here;
-        const int need = k - c_gt;                         // ties to take (>= 1)
-        const float tot = s_gt + (float)need * xk;
-        contrib = side ? w * tot / (float)k : w * (1.f - tot / (float)k);
-        const float gval = (side ? w : -w) / (float)k * L.gscale;
-        int tr = excl;
-        for (int i = i0; i < i1; ++i) {
-          const float v = val[i];
-          bool sel = v > xk;
-          if (v == xk) { sel = tr < need; ++tr; }
-          if (sel && ((mk[i] != 0) == (side == 0))) atomicAdd(&dpx[(long long)i * L.ext_ld + tok], gval);
-        }
-      } else {
-        const float* R = L.refs + ((long long)T.ref * heads + h) * n;
-        float sa = 0.f, sr = 0.f;
-        for (int i = lane; i < n; i += 32) {
-          const float v = mk[i] ? __ldcg(src + i) : 0.f;
-          val[i] = v;
-          sa += v;
-          sr += mk[i] ? R[i] : 0.f;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          sa += __shfl_xor_sync(0xffffffffu, sa, o);
-          sr += __shfl_xor_sync(0xffffffffu, sr, o);
-        }
-        const float A = sa + L.eps, Rs = sr + L.eps;
-        float l1 = 0.f, inner = 0.f;
-        for (int i = lane; i < n; i += 32)
-          if (mk[i]) {
-            const float ah = val[i] / A, df = ah - R[i] / Rs;
-            const float sg = (df > 0.f) - (df < 0.f);
-            l1 += fabsf(df);
-            inner += sg * ah;
-          }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-          inner += __shfl_xor_sync(0xffffffffu, inner, o);
-        }
-        contrib = T.w_ref * l1;
-        for (int i = lane; i < n; i += 32)
-          if (mk[i]) {
-            const float df = val[i] / A - R[i] / Rs;
-            const float sg = (df > 0.f) - (df < 0.f);
-            atomicAdd(&dpx[(long long)i * L.ext_ld + tok], T.w_ref / A * (sg - inner) * L.gscale);
-          }
-      }
-      if (lane == 0 && pid < 160) prob_loss[pid] = contrib;
-      __syncwarp();
+  for (int j = 0; j < PERMAX; ++j) {
+    const int i = i0 + j;
+    q.v[j] = 0.f;
+    q.r[j] = 0.f;
+    if (j < per && i < n) {
+      const uint8_t mb = P.mk[i];
+      q.v[j] = __ldcg(P.src + i);
+      if (P.R) q.r[j] = P.R[i];
+      if (mb) q.m |= 1ull << j;
     }
   }
+}
+
+template <int PERMAX>
+__device__ __forceinline__ float loss_energy(const LossRaw<PERMAX>& q, const LossProb& P, float* dpx, int ext_ld, int n,
+                                             int per, int lane, float gscale) {
+  const int i0 = lane * per;
+  float* dpx_tok = dpx + P.tok;
+  const int k = P.k;
+  // entry: bits 0-15 fp16 pattern of the masked value (0 on the other side of the mask), bit 16 = on this side,
+  // bit 17 = a real element (i < n)
+  uint32_t e[PERMAX];
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j) {
+    uint32_t x = 0u;
+    if (j < per && i0 + j < n) {
+      x = 0x20000u;
+      if ((((q.m >> j) & 1ull) != 0ull) == (P.side == 0))
+        x |= 0x10000u | (uint32_t)__half_as_ushort(__float2half_rn(q.v[j]));
+    }
+    e[j] = x;
+  }
+  // bisection for the k-th largest fp16 bit pattern (non-negative values: unsigned order == numeric order):
+  // invariant count(v >= lo) >= k, count(v >= hi) < k; 15 counting passes over registers
+  uint32_t lo = 0u, hi = 0x7C00u;
+  while (hi - lo > 1u) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < PERMAX; ++j) c += ((e[j] & 0xFFFFu) >= mid);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) lo = mid; else hi = mid;
+  }
+  const float xk = __half2float(__ushort_as_half((unsigned short)lo));
+  int c_gt = 0, ties_here = 0;
+  float s_gt = 0.f;
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j) {
+    const uint32_t bits = e[j] & 0xFFFFu;
+    if (bits > lo) { ++c_gt; s_gt += __half2float(__ushort_as_half((unsigned short)bits)); }
+    ties_here += ((e[j] & 0x20000u) && bits == lo);
+  }
+  c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s_gt += __shfl_xor_sync(0xffffffffu, s_gt, o);
+  int excl = ties_here;                                    // exclusive prefix of tie counts over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, excl, o);
+    if (lane >= o) excl += up;
+  }
+  excl -= ties_here;
+  const int need = k - c_gt;                               // ties to take (>= 1)
+  const float tot = s_gt + (float)need * xk;
+  const float gval = (P.side ? P.w : -P.w) / (float)k * gscale;
+  int tr = excl;
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j) {
+    const uint32_t bits = e[j] & 0xFFFFu;
+    bool sel = bits > lo;
+    if ((e[j] & 0x20000u) && bits == lo) { sel = tr < need; ++tr; }
+    if (sel && (e[j] & 0x10000u)) atomicAdd(dpx_tok + (long long)(i0 + j) * ext_ld, gval);
+  }
+  return P.side ? P.w * tot / (float)k : P.w * (1.f - tot / (float)k);
+}
+
+// reference-attention L1 term: masked, sum-normalised maps compared in L1
+template <int PERMAX>
+__device__ __forceinline__ float loss_ref(const LossRaw<PERMAX>& q, const LossProb& P, float* dpx, int ext_ld, int lane,
+                                          int per, float eps, float gscale) {
+  const int i0 = lane * per;
+  float* dpx_tok = dpx + P.tok;
+  float sa = 0.f, sr = 0.f;
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j)
+    if ((q.m >> j) & 1ull) { sa += q.v[j]; sr += q.r[j]; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+  }
+  const float A = sa + eps, Rs = sr + eps;
+  float l1 = 0.f, inner = 0.f;
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j)
+    if ((q.m >> j) & 1ull) {
+      const float ah = q.v[j] / A, df = ah - q.r[j] / Rs;
+      const float sg = (df > 0.f) - (df < 0.f);
+      l1 += fabsf(df);
+      inner += sg * ah;
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    inner += __shfl_xor_sync(0xffffffffu, inner, o);
+  }
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j)
+    if ((q.m >> j) & 1ull) {
+      const float df = q.v[j] / A - q.r[j] / Rs;
+      const float sg = (df > 0.f) - (df < 0.f);
+      atomicAdd(dpx_tok + (long long)(i0 + j) * ext_ld, P.w / A * (sg - inner) * gscale);
+    }
+  return P.w * l1;
+}
+
+constexpr int kLossScratchBytes = 160 * 4 + 160 * 2 + kMaxSlots * 4 + 16 + kMaxTerms * (int)sizeof(LossTerm);
+
+__device__ __forceinline__ LossProb loss_decode(const XattnLoss& L, const LossTerm* sterms, const int* stok,
+                                                unsigned short code, int bh, int h, int heads, int n) {
+  const LossTerm& T = sterms[code >> 1];
+  const int sub = code & 1;
+  LossProb P;
+  P.src = L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
+  P.mk = L.masks + (long long)T.mask * n;
+  P.tok = stok[T.slot];
+  if (T.type == 0) {
+    P.R = nullptr;
+    P.side = sub;
+    P.k = sub ? T.k_bg : T.k_fg;
+    P.w = sub ? T.w_bg : T.w_fg;
+  } else {
+    P.R = L.refs + ((long long)T.ref * heads + h) * n;
+    P.side = 0;
+    P.k = 1;
+    P.w = T.w_ref;
+  }
+  return P;
+}
+
+template <int PERMAX, bool PIPE>
+__device__ __forceinline__ void loss_problem_loop(const XattnLoss& L, const LossTerm* sterms, const int* stok,
+                                                  const unsigned short* pcode, float* prob_loss, float* dpx, int n_prob,
+                                                  int first, int stride, int lane, int bh, int h, int heads, int n,
+                                                  int per) {
+  if (first >= n_prob) return;
+  LossProb P = loss_decode(L, sterms, stok, pcode[first], bh, h, heads, n);
+  LossRaw<PERMAX> cur;
+  loss_load(cur, P, n, per, lane);
+  for (int pid = first; pid < n_prob; pid += stride) {
+    const bool more = pid + stride < n_prob;
+    LossProb Pn = P;
+    LossRaw<PERMAX> nxt;
+    if (PIPE && more) {                                    // next problem's loads fly during this problem's compute
+      Pn = loss_decode(L, sterms, stok, pcode[pid + stride], bh, h, heads, n);
+      loss_load(nxt, Pn, n, per, lane);
+    }
+    const float contrib = P.R ? loss_ref(cur, P, dpx, L.ext_ld, lane, per, L.eps, L.gscale)
+                              : loss_energy(cur, P, dpx, L.ext_ld, n, per, lane, L.gscale);
+    if (lane == 0) prob_loss[pid] = contrib;
+    if (more) {
+      if (PIPE) {
+        cur = nxt;
+        P = Pn;
+      } else {
+        P = loss_decode(L, sterms, stok, pcode[pid + stride], bh, h, heads, n);
+        loss_load(cur, P, n, per, lane);
+      }
+    }
+  }
+}
+
+// ---- loss reduction of one (image, head), three steps run by 128 threads (4 warps, named barrier 1):
+//   loss_stage : term table, slot->token table and the problem list into shared memory (inputs only: can run early)
+//   loss_zero  : zero rows of dp_extra (must be ordered before any CTA's atomics into them)
+//   loss_run   : this CTA's share of the problems (part of nparts), partial sums combined in a fixed order
+// scratch: kLossScratchBytes of shared memory (16-byte aligned).  n <= 1280, at most 160 problems per image.
+struct LossScratch {
+  float* prob_loss;            // [160] per-problem contributions
+  unsigned short* pcode;       // [160] term*2 + side
+  int* stok;                   // [kMaxSlots] slot -> token
+  int* n_prob;                 // [4] (one used; keeps the table 16-byte aligned)
+  LossTerm* sterms;
+};
+__device__ __forceinline__ LossScratch loss_scratch(float* scratch) {
+  LossScratch S;
+  S.prob_loss = scratch;
+  S.pcode = reinterpret_cast<unsigned short*>(scratch + 160);
+  S.stok = reinterpret_cast<int*>(S.pcode + 160);
+  S.n_prob = S.stok + kMaxSlots;
+  S.sterms = reinterpret_cast<LossTerm*>(S.n_prob + 4);
+  return S;
+}
+static_assert(kLossScratchBytes + 16 <= 4096, "loss scratch");
+
+__device__ __forceinline__ void loss_stage(const XattnLoss& L, float* scratch, int tid, int b) {
+  const int lane = tid & 31;
+  LossScratch S = loss_scratch(scratch);
+  const int t0 = L.img_term_off[b], t1 = L.img_term_off[b + 1];
+  const int nterms = min(t1 - t0, kMaxTerms);
+  {
+    const int* src = reinterpret_cast<const int*>(L.terms + t0);
+    int* dst = reinterpret_cast<int*>(S.sterms);
+    const int words = nterms * (int)(sizeof(LossTerm) / 4);
+    for (int i = tid; i < words; i += 128) dst[i] = src[i];
+    if (tid < kMaxSlots) S.stok[tid] = L.slot_tok[b * kMaxSlots + tid];
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // problem list: energy term -> 2 consecutive ids (fg, bg), reference term -> 1 id.  Every warp builds the same list
+  // (identical values to identical addresses).
+  int n_prob = 0;
+  for (int tb = 0; tb < nterms; tb += 32) {
+    const int t = tb + lane;
+    const int nsub = t < nterms ? ((S.sterms[t].type == 0) ? 2 : 1) : 0;
+    int incl = nsub;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int first = n_prob + incl - nsub;
+    for (int sub = 0; sub < nsub; ++sub)
+      if (first + sub < 160) S.pcode[first + sub] = (unsigned short)(t * 2 + sub);
+    n_prob += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (tid == 0) *S.n_prob = min(n_prob, 160);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__device__ __forceinline__ void loss_zero(const XattnLoss& L, int bh, int n, int row0, int rows, int tid) {
+  float4* d4 = reinterpret_cast<float4*>(L.dp_extra + ((long long)bh * n + row0) * L.ext_ld);
+  const int tot = (rows * L.ext_ld) >> 2;                // ext_ld is a multiple of 4, rows are 16-byte aligned
+  for (int i = tid; i < tot; i += 128) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+#define LOSS_STAMP(i) do { if (dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = t_; } } while (0)
+// part/nparts: the problems are dealt round-robin to nparts CTAs x 4 warps.  With nparts > 1 every CTA leaves its
+// partial in partials[bh*nparts + part] and the last one to arrive (done[bh]) adds them up in part order, so the sum
+// does not depend on arrival order.  done[bh] must be zero on entry.
+__device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int tid, int h, int heads, int bh, int n,
+                                         int part, int nparts, float* partials, int* done,
+                                         unsigned long long* dbg = nullptr) {
+  const int warp = tid >> 5, lane = tid & 31;
+  LossScratch S = loss_scratch(scratch);
+  const int n_prob = *S.n_prob;
+  float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
+  const int per = (n + 31) >> 5;
+  LOSS_STAMP(0);
+  if (per <= 8)
+    loss_problem_loop<8, true>(L, S.sterms, S.stok, S.pcode, S.prob_loss, dpx, n_prob, part * 4 + warp, 4 * nparts,
+                               lane, bh, h, heads, n, per);
+  else
+    loss_problem_loop<40, false>(L, S.sterms, S.stok, S.pcode, S.prob_loss, dpx, n_prob, part * 4 + warp, 4 * nparts,
+                                 lane, bh, h, heads, n, per);
+  LOSS_STAMP(1);
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (tid == 0) {                                          // fixed summation order => deterministic loss
     float acc = 0.f;
-    for (int i = 0; i < n_prob && i < 160; ++i) acc += prob_loss[i];
-    L.loss_part[bh] = acc;
+    for (int i = 0; i < n_prob; ++i)
+      if (((i >> 2) % nparts) == part) acc += S.prob_loss[i];
+    if (nparts == 1) {
+      L.loss_part[bh] = acc;
+    } else {
+      __stcg(partials + bh * nparts + part, acc);
+      __threadfence();
+      if (atomicAdd(done + bh, 1) == nparts - 1) {
+        __threadfence();
+        float tot = 0.f;
+        for (int q = 0; q < nparts; ++q) tot += __ldcg(partials + bh * nparts + q);
+        L.loss_part[bh] = tot;
+      }
+    }
   }
+  LOSS_STAMP(2);
+}
+
+// everything at once (unfused kernel: the last CTA of the (image, head) does it all)
+__device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scratch, float* s_red, int tid, int b,
+                                                  int h, int heads, int bh, int n) {
+  loss_zero(L, bh, n, 0, n, tid);
+  __threadfence_block();
+  loss_stage(L, scratch, tid, b);       // its barriers also order the zero-fill before the atomics
+  loss_run(L, scratch, tid, h, heads, bh, n, 0, 1, nullptr, nullptr);
   (void)s_red;
 }
 

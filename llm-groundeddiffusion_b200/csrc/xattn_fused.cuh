@@ -33,6 +33,9 @@ struct FusedXattnParams {
   int has_loss;
   XattnLoss L;
   int* tile_flags;           // [row tiles] zero on entry: counts the heads of a row tile whose O_h is published
+  int* bh_ready;             // [B*8] zero on entry: row tiles of an (image, head) whose P columns are published
+  int* bh_done;              // [B*8] zero on entry: row tiles of an (image, head) that finished their loss share
+  float* loss_partials;      // [B*8][tiles_per_img]
   unsigned long long* dbg;   // optional [grid][8] %globaltimer stamps (phase timeline), null in production
 };
 
@@ -41,7 +44,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define FUSED_STAMP(i) do { if (p.dbg && threadIdx.x == 64) p.dbg[(long long)blockIdx.x * 8 + (i)] = gtimer(); } while (0)
+#define FUSED_STAMP(i) do { if (p.dbg && threadIdx.x == 64) p.dbg[(long long)blockIdx.x * 16 + (i)] = gtimer(); } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -84,7 +87,7 @@ struct FusedCfg {
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(Q_BYTES + P_BYTES <= RING_BYTES, "core scratch must fit in the stage ring");
   static_assert(128 * (D + 8) * 2 <= RING_BYTES, "epilogue staging must fit in the stage ring");
-  static constexpr int SMEM_BYTES = RING_BYTES + K_BYTES + V_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = RING_BYTES + K_BYTES + V_BYTES + 1024 + 512 + 4096;   // + loss tables
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
@@ -113,6 +116,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_ready + 1);
   int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
   float* s_red = reinterpret_cast<float*>(s_flag + 1);
+  float* sL = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // loss tables (4 KB)
 
   const int warp = threadIdx.x >> 5;
   const int cr = (int)cluster_ctarank();           // rank inside the 4-CTA cluster
@@ -236,6 +240,12 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   };
   float row_m = 0.f, row_l = 1.f;
   if (warp >= 2) {
+    // loss inputs while phase 1 runs on the tensor core: this tile's rows of dp_extra zeroed (ordered before every
+    // CTA's atomics by the publish fence below), term / slot tables and the problem list staged in shared memory
+    if (p.has_loss) {
+      loss_zero(p.L, bh, p.n, tok0, 128, tid);
+      loss_stage(p.L, sL, tid, b);
+    }
     // ---- Q_h: TMEM -> fp16 -> smem A operand (and the optional Q slab for the backward)
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -379,6 +389,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (tid == 0) {
       __threadfence();
       atomicAdd(&p.tile_flags[rt], 1);
+      if (p.has_loss) atomicAdd(&p.bh_ready[bh], 1);
       uint32_t spins = 0;
       while (atomicAdd(&p.tile_flags[rt], 0) < 8) {
         if (++spins > B200_SPIN_LIMIT) __trap();
@@ -437,24 +448,32 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint32_t stgE_s = smem_u32(stgE);
     static_assert(128 * (D + 8) * 2 <= Cfg::K_BYTES + Cfg::V_BYTES, "residual staging must fit in the K/V region");
     if (p.residual) {
-      constexpr int NP = 128 * PPR / 128;              // pieces per thread
-#pragma unroll 1
-      for (int j0 = 0; j0 < NP; j0 += 5) {
-        uint4 tmp[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int pi = tid + (j0 + j) * 128;
-          const int row = pi / PPR, pc = pi - row * PPR;
-          tmp[j] = (j0 + j < NP) ? *reinterpret_cast<const uint4*>(p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8)
-                                 : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int pi = tid + (j0 + j) * 128;
-          const int row = pi / PPR, pc = pi - row * PPR;
-          if (j0 + j < NP) sts128(stgE_s + (row * OLD + pc * 8) * 2, tmp[j]);
-        }
+      // asynchronous copies (LDGSTS): nothing waits on them until the accumulator is needed
+      for (int pi = tid; pi < 128 * PPR; pi += 128) {
+        const int row = pi / PPR, pc = pi - row * PPR;
+        const __half* src = p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stgE_s + (row * OLD + pc * 8) * 2), "l"(src)
+                     : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- guidance loss, overlapped with phase 2 on the tensor core: the row tiles of this (image, head) share the
+    // problems once every tile's P columns are published (fenced before bh_ready went up)
+    if (p.has_loss) {
+      if (tid == 0) {
+        uint32_t spins = 0;
+        while (atomicAdd(&p.bh_ready[bh], 0) < p.tiles_per_img) {
+          if (++spins > B200_SPIN_LIMIT) __trap();
+          __nanosleep(64);
+        }
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      loss_run(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, p.loss_partials, p.bh_done,
+               p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr);
+    }
+    if (p.residual) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     mbar_wait(acc_full, 1);   // fourth completion
@@ -492,21 +511,6 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     tc_fence_before();
 
-    // ---- guidance loss: the last CTA of this (image, head) reduces (P columns were published before phase 2)
-    if (p.has_loss) {
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid == 0) {
-        const int old = atomicAdd(&p.L.counters[bh], 1);
-        *s_flag = (old == p.tiles_per_img - 1);
-        if (old == p.tiles_per_img - 1) p.L.counters[bh] = 0;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*s_flag) {
-        __threadfence();
-        xattn_loss_reduce(p.L, reinterpret_cast<float*>(sK), s_red, tid, b, h, 8, bh, p.n);
-      }
-    }
   }
   FUSED_STAMP(7);
   __syncthreads();

@@ -42,5 +42,18 @@ elif case == "attn":
     k[:, :, d:] = 0
     for _ in range(3):
         ops.attention_fwd(q, k, vt, B, heads, n, n, d, d ** -0.5)
+elif case == "qkv320":
+    B, heads, d, n, C = 16, 8, 40, 4096, 320
+    x, w = torch.randn(B * n, C, device=dev).half(), torch.randn(3 * C, C, device=dev).half()
+    q, k, vt = ops.alloc_head_slabs(B, heads, d, n, n, dev)
+    for _ in range(3):
+        ops.project_heads(x, w, n, heads, d, 0, q, k, vt)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.project_heads(x, w, n, heads, d, 0, q, k, vt)
+    e1.record()
+    torch.cuda.synchronize()
+    print("qkv320 ms", e0.elapsed_time(e1) / 10)
 torch.cuda.synchronize()
 print("done", case)

@@ -16,20 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--fuser", type=int, default=1)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--tiny", type=int, default=0)
-    a = ap.parse_args()
+def setup(batch=8, fuser=1, tiny=0):
     import lgd_b200  # noqa: F401
     from lgd_b200 import guidance as G, pipelines as P, weights as Wt
     from lgd_b200.unet import B200UNet, UNetConfig
     dev = torch.device("cuda:0")
-    cfg = UNetConfig.tiny(gligen=True) if a.tiny else UNetConfig.sd15(gligen=True)
+    cfg = UNetConfig.tiny(gligen=True) if tiny else UNetConfig.sd15(gligen=True)
     net = B200UNet(cfg, Wt.synthetic_weights(cfg, 0, dev), dev)
-    B, side = a.batch, 64
+    B, side = batch, 64
     g = torch.Generator().manual_seed(0)
     z = torch.randn(B, 4, side, side, generator=g).to(dev)
     text = torch.randn(2 * B, 77, 768, generator=g)
@@ -55,18 +49,38 @@ def main():
     t2 = torch.full((2 * B,), 500.0, device=dev)
     t1 = torch.full((B,), 500.0, device=dev)
 
+    return dict(net=net, z=z, t2=t2, t1=t1, kv=kv, kv_cond=kv_cond, losses=losses, objs=objs, B=B, fuser=bool(fuser))
+
+
+def run_phase(c, phase):
+    net, B = c["net"], c["B"]
+    if phase == "forward":
+        net.forward(c["z"], c["t2"], c["kv"], rep=2, objs=c["objs"], fuser_on=c["fuser"])
+    else:
+        net.guidance_gradient(c["z"], c["t1"], c["kv_cond"], c["losses"], objs=c["objs"][:B * 30], fuser_on=c["fuser"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--fuser", type=int, default=1)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--tiny", type=int, default=0)
+    a = ap.parse_args()
+    c = setup(a.batch, a.fuser, a.tiny)
+
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
     for rep in range(a.reps):
         e = [ev() for _ in range(3)]
         e[0].record()
-        net.forward(z, t2, kv, rep=2, objs=objs, fuser_on=bool(a.fuser))
+        run_phase(c, "forward")
         e[1].record()
-        net.guidance_gradient(z, t1, kv_cond, losses, objs=objs[:B * 30], fuser_on=bool(a.fuser))
+        run_phase(c, "guidance")
         e[2].record()
         torch.cuda.synchronize()
-        print(f"rep {rep}: CFG forward (batch {2 * B}) {e[0].elapsed_time(e[1]):.2f} ms, guidance fwd+bwd (batch {B}) "
+        print(f"rep {rep}: CFG forward (batch {2 * c['B']}) {e[0].elapsed_time(e[1]):.2f} ms, guidance fwd+bwd (batch {c['B']}) "
               f"{e[1].elapsed_time(e[2]):.2f} ms")
 
 

@@ -1,4 +1,5 @@
-"""phase timeline of xattn_fused_kernel from in-kernel %globaltimer stamps (B=8, n=256, C=1280): per-CTA phase durations"""
+"""phase timeline of xattn_fused_kernel from in-kernel %globaltimer stamps (B=8, n=256, C=1280): per-CTA phase times;
+slots 8..10 are the loss reduction's own stamps"""
 import ctypes
 import os
 import sys
@@ -11,16 +12,22 @@ import bench  # noqa: E402
 from lgd_b200._lib import lib  # noqa: E402
 
 dev = torch.device("cuda:0")
-dbg = torch.zeros(128 * 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(128 * 16, dtype=torch.int64, device=dev)
 for wl in (False, True):
+    dbg.zero_()
     lib().b200lmd_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
     r = bench.xattn_roofline(dev, with_loss=wl)
     torch.cuda.synchronize()
-    t = dbg.view(128, 8).cpu().double()
+    t = dbg.view(128, 16).cpu().double()
     t0 = t[:, 0].min()
-    rel = (t - t0) / 1e3
-    names = ["start", "Q acc done", "S done", "O done", "pre-sync2", "post-sync2", "out acc done", "end"]
+    names = ["start", "Q acc done", "S done", "O done", "pre-sync2", "post-sync2", "out acc done", "end",
+             "loss run", "loss probs", "loss end"]
     print("with_loss", wl, "ms_per_op", r["ms_per_op"])
     for i, nme in enumerate(names):
-        print(f"  {nme:14s} min {rel[:, i].min():8.2f}  median {rel[:, i].median():8.2f}  max {rel[:, i].max():8.2f} us")
+        col = t[:, i]
+        col = col[col > 0]
+        if col.numel() == 0:
+            continue
+        rel = (col - t0) / 1e3
+        print(f"  {nme:14s} n={col.numel():3d} min {rel.min():8.2f}  median {rel.median():8.2f}  max {rel.max():8.2f} us")
 lib().b200lmd_set_debug_buffer(None)
