@@ -88,7 +88,7 @@ def peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one xattn_fused_kernel launch at this shape, from the ncu --set full
 # capture summarised in profiles/ (None until captured)
-XATTN_DRAM_BYTES_NCU = None
+XATTN_DRAM_BYTES_NCU = 20.76e6     # dram__bytes_read+write per launch, profiles/r1_ncu_summary.md (ncu --set full)
 
 
 def xattn_roofline(dev, with_loss=True):

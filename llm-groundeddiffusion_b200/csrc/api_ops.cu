@@ -214,8 +214,9 @@ extern "C" int b200lmd_attention_fwd_f16(const void* q, const void* k, const voi
 }
 
 static int gn_rows_per(int B, int n) {
-  // aim for ~2 waves of blocks over (chunks x B)
-  int chunks = (2 * kNumSMs + B - 1) / B;
+  // aim for ~4 blocks per SM over (chunks x B): several 256-thread blocks are resident per SM and hide each other's
+  // load latency
+  int chunks = (4 * kNumSMs + B - 1) / B;
   int rp = (n + chunks - 1) / chunks;
   return rp < 4 ? 4 : rp;
 }
@@ -229,9 +230,10 @@ extern "C" int b200lmd_groupnorm_f16(const void* x, const void* gamma, const voi
     const int rp = gn_rows_per(B, n);
     dim3 grid((n + rp - 1) / rp, B);
     gn_stats_kernel<<<grid, 256, groups * 2 * sizeof(float), st>>>((const __half*)x, (float*)sums, n, C, groups, rp);
-    gn_apply_kernel<<<ew_grid((long long)B * n * (C / 8)), 256, 0, st>>>((const __half*)x, (const float*)sums,
-                                                                        (const float*)gamma, (const float*)beta,
-                                                                        (__half*)y, B, n, C, groups, eps, silu);
+    if (2 * C * sizeof(float) > 48 * 1024) throw std::runtime_error("GroupNorm: C too large for the scale/shift table");
+    gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>((const __half*)x, (const float*)sums,
+                                                              (const float*)gamma, (const float*)beta, (__half*)y, B, n,
+                                                              C, groups, eps, silu, rp);
     B200_CHECK(cudaGetLastError());
   });
 }
@@ -248,9 +250,9 @@ extern "C" int b200lmd_groupnorm_bwd_f16(const void* dy, const void* x, const vo
                                                                       (const float*)sums, (const float*)gamma,
                                                                       (const float*)beta, (float*)bsums, n, C, groups,
                                                                       eps, silu, rp);
-    gn_bwd_apply_kernel<<<ew_grid((long long)B * n * (C / 8)), 256, 0, st>>>(
+    gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(
         (const __half*)dy, (const __half*)x, (const float*)sums, (const float*)bsums, (const float*)gamma,
-        (const float*)beta, (__half*)dx, B, n, C, groups, eps, silu, accumulate);
+        (const float*)beta, (__half*)dx, B, n, C, groups, eps, silu, accumulate, rp);
     B200_CHECK(cudaGetLastError());
   });
 }

@@ -160,26 +160,27 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         const int kbase = j * 128;
         const bool full = (kbase + 128 <= p.nk);
+        // ---- the whole score row of this tile in registers: one TMEM read (four loads in flight, one wait)
+        uint32_t v[128];
+        tmem_ld_x32(tS[t] + lane_off, v);
+        tmem_ld_x32(tS[t] + lane_off + 32, v + 32);
+        tmem_ld_x32(tS[t] + lane_off + 64, v + 64);
+        tmem_ld_x32(tS[t] + lane_off + 96, v + 96);
+        tmem_ld_wait();
         // ---- tile maximum (4 independent chains)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(tS[t] + lane_off + c0, v);
-          tmem_ld_wait();
-          if (full) {
+        if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-              mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-              mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-              mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (kbase + c0 + i < p.nk) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+          for (int i = 0; i < 128; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (kbase + i < p.nk) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
         }
         const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
         const bool need = m_tile > m_ref + 8.f;
@@ -206,16 +207,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_ref = m_new;
         // ---- P = 2^(s' - m_ref) -> fp16 smem, row sum
         float a0 = 0.f, a1 = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(tS[t] + lane_off + c0, v);
-          tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_ref));
-            float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_ref));
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[c0 + 2 * i]), p.scale_log2, -m_ref));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[c0 + 2 * i + 1]), p.scale_log2, -m_ref));
             if (!full) {
               if (kbase + c0 + 2 * i >= p.nk) e0 = 0.f;
               if (kbase + c0 + 2 * i + 1 >= p.nk) e1 = 0.f;

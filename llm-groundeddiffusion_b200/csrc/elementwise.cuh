@@ -54,12 +54,18 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   const int vecs = C >> 3;
   const int r0 = blockIdx.x * rows_per;
   const int r1 = min(n, r0 + rows_per);
-  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+  // threads as (rows in flight) x (8-channel vectors of a row): every thread streams, loads of a warp are contiguous
+  const int tpr = min(vecs, (int)blockDim.x);
+  const int rif = blockDim.x / tpr;
+  const int tr = threadIdx.x / tpr, tv = threadIdx.x - tr * tpr;
+  for (int v = tv; v < vecs && tr < rif; v += tpr) {
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-    const __half* base = x + ((long long)b * n + r0) * C + v * 8;
-    for (int r = r0; r < r1; ++r, base += C) {
+    const __half* base = x + ((long long)b * n + r0 + tr) * C + v * 8;
+    const long long step = (long long)rif * C;
+#pragma unroll 4
+    for (int r = r0 + tr; r < r1; r += rif, base += step) {
       float f[8];
       unpack8(*reinterpret_cast<const uint4*>(base), f);
 #pragma unroll
@@ -94,29 +100,51 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
 // y = silu?( (x - mean) * rstd * gamma + beta ), fp16 out.  sums -> mean/rstd on the fly.
 __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ sums,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __half* __restrict__ y, int B, int n, int C, int groups, float eps, int do_silu) {
+                                __half* __restrict__ y, int B, int n, int C, int groups, float eps, int do_silu,
+                                int rows_per) {
+  // grid = (chunks, B).  Per-channel scale / shift of image b once per block (shared memory), then a pure
+  // fma (+ silu) stream with the same (rows in flight) x (vectors of a row) thread layout as the statistics pass.
+  extern __shared__ float s_ss[];   // [C] scale, [C] shift
+  float* s_scale = s_ss;
+  float* s_shift = s_ss + C;
+  const int b = blockIdx.y;
   const int cpg = C / groups;
   const int vecs = C >> 3;
-  const long long total = (long long)B * n * vecs;
   const float inv_cnt = 1.f / ((float)n * cpg);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vecs);
-    const long long row = i / vecs;
-    const int b = (int)(row / n);
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + row * C + v * 8), f);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = sums[((long long)b * groups + g) * 2] * inv_cnt;
+    const float var = sums[((long long)b * groups + g) * 2 + 1] * inv_cnt - mean * mean;
+    const float sc = rsqrtf(fmaxf(var, 0.f) + eps) * gamma[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - mean * sc;
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per;
+  const int r1 = min(n, r0 + rows_per);
+  const int tpr = min(vecs, (int)blockDim.x);
+  const int rif = blockDim.x / tpr;
+  const int tr = threadIdx.x / tpr, tv = threadIdx.x - tr * tpr;
+  for (int v = tv; v < vecs && tr < rif; v += tpr) {
+    float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
-      const float mean = sums[((long long)b * groups + g) * 2] * inv_cnt;
-      const float var = sums[((long long)b * groups + g) * 2 + 1] * inv_cnt - mean * mean;
-      const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
-      float t = (f[j] - mean) * rstd * gamma[c] + beta[c];
-      f[j] = do_silu ? silu_f(t) : t;
+      sc[j] = s_scale[v * 8 + j];
+      sh[j] = s_shift[v * 8 + j];
     }
-    *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(f);
+    long long off = ((long long)b * n + r0 + tr) * C + v * 8;
+    const long long step = (long long)rif * C;
+#pragma unroll 4
+    for (int r = r0 + tr; r < r1; r += rif, off += step) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + off), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(f[j], sc[j], sh[j]);
+        f[j] = do_silu ? silu_f(t) : t;
+      }
+      *reinterpret_cast<uint4*>(y + off) = pack8(f);
+    }
   }
 }
 
@@ -135,7 +163,10 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
   const int r0 = blockIdx.x * rows_per;
   const int r1 = min(n, r0 + rows_per);
   const float inv_cnt = 1.f / ((float)n * cpg);
-  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+  const int tpr = min(vecs, (int)blockDim.x);
+  const int rif = blockDim.x / tpr;
+  const int tr = threadIdx.x / tpr, tv = threadIdx.x - tr * tpr;
+  for (int v = tv; v < vecs && tr < rif; v += tpr) {
     float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -149,7 +180,8 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
       s1[j] = s2[j] = 0.f;
     }
     const long long off0 = ((long long)b * n + r0) * C + v * 8;
-    for (int r = r0; r < r1; ++r) {
+#pragma unroll 2
+    for (int r = r0 + tr; r < r1; r += rif) {
       float fx[8], fd[8];
       const long long off = off0 + (long long)(r - r0) * C;
       unpack8(*reinterpret_cast<const uint4*>(x + off), fx);
@@ -180,36 +212,51 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
                                     const float* __restrict__ sums, const float* __restrict__ bsums,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     __half* __restrict__ dx, int B, int n, int C, int groups, float eps, int do_silu,
-                                    int accumulate) {
+                                    int accumulate, int rows_per) {
+  // grid = (chunks, B); per-channel constants live in registers across the row walk (same thread layout as the
+  // statistics pass)
+  const int b = blockIdx.y;
   const int cpg = C / groups;
   const int vecs = C >> 3;
-  const long long total = (long long)B * n * vecs;
   const float inv_cnt = 1.f / ((float)n * cpg);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vecs);
-    const long long row = i / vecs;
-    const int b = (int)(row / n);
-    float fx[8], fd[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + row * C + v * 8), fx);
-    unpack8(*reinterpret_cast<const uint4*>(dy + row * C + v * 8), fd);
-    if (accumulate) unpack8(*reinterpret_cast<const uint4*>(dx + row * C + v * 8), o);
+  const int r0 = blockIdx.x * rows_per;
+  const int r1 = min(n, r0 + rows_per);
+  const int tpr = min(vecs, (int)blockDim.x);
+  const int rif = blockDim.x / tpr;
+  const int tr = threadIdx.x / tpr, tv = threadIdx.x - tr * tpr;
+  for (int v = tv; v < vecs && tr < rif; v += tpr) {
+    float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = v * 8 + j;
-      const int g = c / cpg;
-      const long long sg = ((long long)b * groups + g) * 2;
-      const float mean = sums[sg] * inv_cnt;
-      const float var = sums[sg + 1] * inv_cnt - mean * mean;
-      const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
-      const float xh = (fx[j] - mean) * rstd;
-      float d = fd[j];
-      if (do_silu) d *= silu_grad(xh * gamma[c] + beta[c]);
-      d *= gamma[c];
-      const float r = rstd * (d - bsums[sg] * inv_cnt - xh * bsums[sg + 1] * inv_cnt);
-      o[j] = accumulate ? o[j] + r : r;
+      const long long sg = ((long long)b * groups + c / cpg) * 2;
+      mean[j] = sums[sg] * inv_cnt;
+      const float var = sums[sg + 1] * inv_cnt - mean[j] * mean[j];
+      rstd[j] = rsqrtf(fmaxf(var, 0.f) + eps);
+      ga[j] = gamma[c];
+      be[j] = beta[c];
+      m1[j] = bsums[sg] * inv_cnt;
+      m2[j] = bsums[sg + 1] * inv_cnt;
     }
-    *reinterpret_cast<uint4*>(dx + row * C + v * 8) = pack8(o);
+    long long off = ((long long)b * n + r0 + tr) * C + v * 8;
+    const long long step = (long long)rif * C;
+#pragma unroll 2
+    for (int r = r0 + tr; r < r1; r += rif, off += step) {
+      float fx[8], fd[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + off), fx);
+      unpack8(*reinterpret_cast<const uint4*>(dy + off), fd);
+      if (accumulate) unpack8(*reinterpret_cast<const uint4*>(dx + off), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (fx[j] - mean[j]) * rstd[j];
+        float d = fd[j];
+        if (do_silu) d *= silu_grad(xh * ga[j] + be[j]);
+        d *= ga[j];
+        const float rr = rstd[j] * (d - m1[j] - xh * m2[j]);
+        o[j] = accumulate ? o[j] + rr : rr;
+      }
+      *reinterpret_cast<uint4*>(dx + off) = pack8(o);
+    }
   }
 }
 
@@ -225,6 +272,49 @@ __global__ void ln_fwd_kernel(const __half* __restrict__ x, const float* __restr
        row += (long long)gridDim.x * warps) {
     const __half* xr = x + row * C;
     float s = 0.f, q = 0.f;
+    if (vecs <= 5 * 32) {
+      // the row stays in registers between the statistics and the normalisation: one global read (C <= 1280)
+      uint4 buf[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int v = lane + 32 * k;
+        buf[k] = v < vecs ? *reinterpret_cast<const uint4*>(xr + v * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        float f[8];
+        unpack8(buf[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s += f[j];
+          q += f[j] * f[j];
+        }
+      }
+      s = warp_sum(s);
+      q = warp_sum(q);
+      const float mean = s / C;
+      const float rstd = rsqrtf(fmaxf(q / C - mean * mean, 0.f) + eps);
+      if (stats && lane == 0) {
+        stats[row * 2] = mean;
+        stats[row * 2 + 1] = rstd;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int v = lane + 32 * k;
+        if (v < vecs) {
+          float f[8];
+          unpack8(buf[k], f);
+          const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
+          *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(f);
+        }
+      }
+      continue;
+    }
     for (int v = lane; v < vecs; v += 32) {
       float f[8];
       unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f);

@@ -163,6 +163,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) fn(ew * 16 + rr * 4 + (lane >> 3), lane & 7, orws[rr]);
       };
+      // EPI_HEADS: (image, token) of the rows this thread touches, once per tile (32-bit: M < 2^31)
+      int pim[4] = {0, 0, 0, 0}, ptok[4] = {0, 0, 0, 0}, tok_me = 0;
+      if (p.mode == EPI_HEADS) {
+        const unsigned rpi = (unsigned)p.rows_per_img;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const unsigned o = orws[rr] >= 0 ? (unsigned)orws[rr] : 0u;
+          pim[rr] = (int)(o / rpi);
+          ptok[rr] = (int)(o - (unsigned)pim[rr] * rpi);
+        }
+        tok_me = (int)(orow - (long long)img * p.rows_per_img);
+      }
       // residual / accumulate operand: fetched one chunk ahead into registers so its latency hides behind the
       // accumulator wait and the previous chunk's arithmetic
       const bool rd = (p.mode == EPI_ROWMAJOR) && ((p.residual != nullptr) || p.accumulate_out);
@@ -264,19 +276,29 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                    make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])));
           }
           if (p.mode == EPI_HEADS) {
-            // transposed slabs: this thread's row is one token, lanes of a warp are consecutive tokens -> coalesced
-            const int tok = (int)(orow % p.rows_per_img);
+            // transposed slabs: this thread's row is one token, lanes of a warp are consecutive tokens -> coalesced.
+            // (projection, head, column-in-head) of the first 8-column group, then stepped without divisions
             if (row_ok) {
+              int which = nh / p.C;
+              const int cc = nh - which * p.C;
+              int head = cc / p.d, j0 = cc - head * p.d;
+              which += p.which0;
 #pragma unroll 1
               for (int g = 0; g < 4; ++g) {
-                const int n = nh + g * 8;
-                if (n >= p.N) break;
-                const int which = p.which0 + n / p.C;
-                if (!p.tr[which]) continue;
-                const int cc = n % p.C, head = cc / p.d, j0 = cc % p.d;
-                __half* dst = p.tr[which] + (((long long)img * p.heads + head) * p.d16 + j0) * (long long)p.tr_alloc[which] + tok;
+                if (nh + g * 8 >= p.N) break;
+                if (p.tr[which]) {
+                  const long long ta = p.tr_alloc[which];
+                  __half* dst = p.tr[which] + (((long long)img * p.heads + head) * p.d16 + j0) * ta + tok_me;
+                  const uint4 pk = lds128(my_s + g * 16);
+                  const __half* hv = reinterpret_cast<const __half*>(&pk);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[(long long)j * p.tr_alloc[which]] = my[g * 8 + j];
+                  for (int j = 0; j < 8; ++j) dst[j * ta] = hv[j];
+                }
+                j0 += 8;
+                if (j0 >= p.d) {
+                  j0 = 0;
+                  if (++head == p.heads) { head = 0; ++which; }
+                }
               }
             }
           }
@@ -294,16 +316,23 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             });
           } else {  // EPI_HEADS row-major slabs: 16-byte pieces never straddle a head (d % 8 == 0)
-            for_pieces([&](int row, int pc, long long orw) {
-              const int n = nb + pc * 8;
-              if (orw < 0 || n >= p.N) return;
-              const int which = p.which0 + n / p.C;
-              if (!p.rm[which]) return;
-              const int cc = n % p.C, head = cc / p.d, j0 = cc % p.d;
-              const int im = (int)(orw / p.rows_per_img), tok = (int)(orw % p.rows_per_img);
-              *reinterpret_cast<uint4*>(p.rm[which] + (((long long)im * p.heads + head) * p.rm_alloc[which] + tok) * (long long)p.dp + j0) =
-                  lds128(stg_s + (row * LD + pc * 8) * 2);
-            });
+            const int n = nb + (lane & 7) * 8;            // the same column group for this thread's four rows
+            if (n < p.N) {
+              const int wh = n / p.C;
+              const int cc = n - wh * p.C;
+              const int head = cc / p.d, j0 = cc - head * p.d;
+              const int which = p.which0 + wh;
+              if (p.rm[which]) {
+                const long long ra = p.rm_alloc[which];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                  if (orws[rr] < 0) continue;
+                  const int row = ew * 16 + rr * 4 + (lane >> 3);
+                  *reinterpret_cast<uint4*>(p.rm[which] + (((long long)pim[rr] * p.heads + head) * ra + ptok[rr]) * (long long)p.dp + j0) =
+                      lds128(stg_s + (row * LD + (lane & 7) * 8) * 2);
+                }
+              }
+            }
           }
         }
       }

@@ -41,7 +41,7 @@ class LibProxy:
     def __getattr__(self, name):
         if name not in self._cache:
             f = getattr(self._lib, name)
-            self._cache[name] = self._rec.wrap(f, lambda *a, _n=name, **k: (_n,)) if name.startswith("b200lmd_") else f
+            self._cache[name] = self._rec.wrap(f, lambda *a, _n=name, **k: (_n,)) if name.startswith("b200lmd_") and name not in ("b200lmd_gemm", "b200lmd_round_dp", "b200lmd_round_d16") else f
         return self._cache[name]
 
 
