@@ -44,7 +44,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = kv_empty + STAGES;    // 2 (per query tile)
   uint64_t* p_full = s_full + 2;           // 2
   uint64_t* pv_done = p_full + 2;          // 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_free = pv_done + 2;          // 2: the score row of step j sits in registers, S(j+1) may overwrite TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * 256;
@@ -68,6 +69,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&s_full[t], 1);
         mbar_init(&p_full[t], 4);
         mbar_init(&pv_done[t], 1);
+        mbar_init(&s_free[t], 4);
       }
       fence_barrier_init();
     }
@@ -132,17 +134,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int t = 0; t < ntile; ++t) issue_S(t, 0);
     for (int j = 0; j < nkv; ++j) {
       const int stage = j % STAGES;
+      // S(j+1) is issued as soon as the softmax warps hold S(j) in registers: it runs under their exponentials, so
+      // the next score tile is ready the moment they finish the current one
+      if (j + 1 < nkv) {
+        mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
+        for (int t = 0; t < ntile; ++t) {
+          mbar_wait(&s_free[t], j & 1);
+          tc_fence_after();
+          issue_S(t, j + 1);
+        }
+      }
       for (int t = 0; t < ntile; ++t) {
         mbar_wait(&p_full[t], j & 1);
         tc_fence_after();
         issue_PV(t, j);
-        if (j + 1 < nkv) {
-          if (t == 0) {
-            mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
-            tc_fence_after();
-          }
-          issue_S(t, j + 1);
-        }
       }
       if (elect_one()) tc_commit(&kv_empty[stage]);   // every MMA that read stage j has been issued before this
       __syncwarp();
@@ -167,15 +172,18 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_x32(tS[t] + lane_off + 64, v + 64);
         tmem_ld_x32(tS[t] + lane_off + 96, v + 96);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&s_free[t]);
         // ---- tile maximum (4 independent chains)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+          for (int i = 0; i < 128; i += 8) {
+            mx0 = max3(mx0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            mx1 = max3(mx1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            mx2 = max3(mx2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            mx3 = max3(mx3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
           }
         } else {
 #pragma unroll
@@ -275,16 +283,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 template <int D16>
 inline void launch_attn_fwd2_t(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVt,
                                const AttnParams& p, int nq, int BH, cudaStream_t st) {
-  using Cfg = Attn2Cfg<D16, 2>;
+  using Cfg = Attn2Cfg<D16, 3>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
   static_assert(256 + 2 * Cfg::O_STRIDE <= 512, "TMEM budget");
   static bool done = false;
   if (!done) {
-    cudaFuncSetAttribute(attn_fwd2_kernel<D16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(attn_fwd2_kernel<D16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     done = true;
   }
   dim3 grid((nq + 255) / 256, BH, 1);
-  attn_fwd2_kernel<D16, 2><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmVt, p);
+  attn_fwd2_kernel<D16, 3><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmVt, p);
 }
 
 }  // namespace b200

@@ -127,15 +127,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(q_full, 0);
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < total; ++it) {
+    // S / dP of tile it+1 are issued as soon as the softmax warps hold tile it in registers (sdp_empty), i.e. they run
+    // under the element-wise work of tile it; dQ(it) follows when dS(it) is in shared memory.
+    auto issue_sdp = [&](int it, int stage) {
       const bool pass_b = it >= first_b;
-      const int j = it - first_b;  // tile index inside pass B
-      mbar_wait(&kv_full[stage], phase);
-      mbar_wait(sdp_empty, (it & 1) ^ 1);
-      tc_fence_after();
       const uint32_t kaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES);
       const uint32_t vaddr = kaddr + Cfg::K_BYTES;
-      const uint32_t ktaddr = vaddr + Cfg::K_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int a = 0; a < DPB; ++a) {
@@ -157,6 +154,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (!pass_b) tc_commit(&kv_empty[stage]);  // pass A: the stage is free once S / dP exist
       }
       __syncwarp();
+    };
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_sdp(0, 0);
+    for (int it = 0; it < total; ++it) {
+      const bool pass_b = it >= first_b;
+      const int j = it - first_b;  // tile index inside pass B
+      const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+      const uint32_t nphase = (nstage == 0) ? (phase ^ 1) : phase;
+      if (it + 1 < total) {
+        mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(sdp_empty, it & 1);
+        tc_fence_after();
+        issue_sdp(it + 1, nstage);
+      }
+      const uint32_t ktaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES) + 2 * Cfg::K_BYTES;
       if (pass_b) {
         mbar_wait(ds_full, j & 1);
         tc_fence_after();
@@ -174,7 +187,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
       }
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      stage = nstage;
+      phase = nphase;
     }
   } else {
     const int quad = warp & 3;
@@ -216,30 +230,52 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane_id() == 0) mbar_arrive(sdp_empty);
         continue;
       }
+      // this warp's half of the S / dP rows into registers in one go, then TMEM is free for the next tile's MMAs
+      constexpr int CW = KVT / 2;
+      const int cb = grp * CW;
+      uint32_t s[CW], g[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 32) {
+        tmem_ld_x32(tS + lane_off + cb + c, s + c);
+        if (p.has_dO) tmem_ld_x32(tdP + lane_off + cb + c, g + c);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(sdp_empty);
+      const bool full = ok && (kbase + KVT <= p.nk) && (ext == nullptr);
       mbar_wait(ds_empty, (j & 1) ^ 1);
-#pragma unroll 1
-      for (int c0 = grp * (KVT / 2); c0 < (grp + 1) * (KVT / 2); c0 += 32) {
-        uint32_t s[32], g[32];
-        tmem_ld_x32(tS + lane_off + c0, s);
-        if (p.has_dO) tmem_ld_x32(tdP + lane_off + c0, g);
-        tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < CW; c += 32) {
+        const int c0 = cb + c;
         uint32_t pk[16];
+        if (full) {       // interior tile, no loss gradient: pure arithmetic
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float o2[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int kk = kbase + c0 + 2 * i + e;
-            float v = 0.f;
-            if (ok && kk < p.nk) {
-              const float pr = exp2f(__uint_as_float(s[2 * i + e]) * p.scale_log2 - L2);
-              float dp = p.has_dO ? __uint_as_float(g[2 * i + e]) : 0.f;
-              if (ext) dp += ext[kk];
-              v = pr * (dp - delta) * p.scale;
-            }
-            o2[e] = v;
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c + 2 * i]), p.scale_log2, -L2));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 2 * i + 1]), p.scale_log2, -L2));
+            const float d0 = (p.has_dO ? __uint_as_float(g[c + 2 * i]) : 0.f) - delta;
+            const float d1 = (p.has_dO ? __uint_as_float(g[c + 2 * i + 1]) : 0.f) - delta;
+            pk[i] = pack_h2(p0 * d0 * p.scale, p1 * d1 * p.scale);
           }
-          pk[i] = pack_h2(o2[0], o2[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float o2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int kk = kbase + c0 + 2 * i + e;
+              float v = 0.f;
+              if (ok && kk < p.nk) {
+                const float pr = ex2_approx(fmaf(__uint_as_float(s[c + 2 * i + e]), p.scale_log2, -L2));
+                float dp = p.has_dO ? __uint_as_float(g[c + 2 * i + e]) : 0.f;
+                if (ext) dp += ext[kk];
+                v = pr * (dp - delta) * p.scale;
+              }
+              o2[e] = v;
+            }
+            pk[i] = pack_h2(o2[0], o2[1]);
+          }
         }
         uint8_t* atom = sdS + (c0 >> 6) * 16384;
         const int ch0 = (c0 & 63) >> 3;
@@ -251,10 +287,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) {
-        mbar_arrive(sdp_empty);
-        mbar_arrive(ds_full);
-      }
+      if (lane_id() == 0) mbar_arrive(ds_full);
     }
     mbar_wait(dq_full, 0);
     tc_fence_after();
@@ -390,14 +423,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     mbar_wait(kv_full, 0);
     int stage = 0;
     uint32_t phase = 0;
-    for (int i = 0; i < nqt; ++i) {
-      mbar_wait(&q_full[stage], phase);
-      mbar_wait(sdp_empty, (i & 1) ^ 1);
-      tc_fence_after();
+    // S^T / dP^T of query tile i+1 are issued as soon as the softmax warps hold tile i in registers (sdp_empty)
+    auto issue_sdp = [&](int stage) {
       const uint32_t qaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES);
       const uint32_t oaddr = qaddr + Cfg::Q_BYTES;
-      const uint32_t qtaddr = oaddr + Cfg::Q_BYTES;
-      const uint32_t otaddr = qtaddr + Cfg::T_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int a = 0; a < DPB; ++a) {
@@ -414,6 +443,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tc_commit(sdp_full);
       }
       __syncwarp();
+    };
+    mbar_wait(&q_full[0], 0);
+    tc_fence_after();
+    issue_sdp(0);
+    for (int i = 0; i < nqt; ++i) {
+      const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+      const uint32_t nphase = (nstage == 0) ? (phase ^ 1) : phase;
+      if (i + 1 < nqt) {
+        mbar_wait(&q_full[nstage], nphase);
+        mbar_wait(sdp_empty, i & 1);
+        tc_fence_after();
+        issue_sdp(nstage);
+      }
+      const uint32_t qtaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES) + 2 * Cfg::Q_BYTES;
+      const uint32_t otaddr = qtaddr + Cfg::T_BYTES;
       mbar_wait(pt_full, i & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -434,7 +478,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         if (i == nqt - 1) tc_commit(out_full);
       }
       __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      stage = nstage;
+      phase = nphase;
     }
   } else {
     const int quad = warp & 3;
@@ -454,14 +499,25 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, i & 1);
-      mbar_wait(pt_empty, (i & 1) ^ 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = grp * (QT / 2); c0 < (grp + 1) * (QT / 2); c0 += 32) {
-        uint32_t s[32], g[32];
-        tmem_ld_x32(tST + lane_off + c0, s);
-        tmem_ld_x32(tdPT + lane_off + c0, g);
-        tmem_ld_wait();
+      // this warp's half of the S^T / dP^T rows into registers, then TMEM is free for the next query tile's MMAs
+      constexpr int CW = QT / 2;
+      const int cb = grp * CW;
+      uint32_t s[CW], g[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 32) {
+        tmem_ld_x32(tST + lane_off + cb + c, s + c);
+        tmem_ld_x32(tdPT + lane_off + cb + c, g + c);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(sdp_empty);
+      const bool full = kok && ((i + 1) * QT <= p.nq);
+      mbar_wait(pt_empty, (i & 1) ^ 1);
+#pragma unroll
+      for (int cc = 0; cc < CW; cc += 32) {
+        const int c0 = cb + cc;
         uint32_t pp[16], ds[16];
 #pragma unroll
         for (int e2 = 0; e2 < 16; ++e2) {
@@ -470,9 +526,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           for (int e = 0; e < 2; ++e) {
             const int c = c0 + 2 * e2 + e;
             float pr = 0.f, dsv = 0.f;
-            if (kok && (i * QT + c) < p.nq) {
-              pr = exp2f(__uint_as_float(s[2 * e2 + e]) * p.scale_log2 - L[c]);
-              dsv = pr * (__uint_as_float(g[2 * e2 + e]) - Dd[c]) * p.scale;
+            if (full || (kok && (i * QT + c) < p.nq)) {
+              pr = ex2_approx(fmaf(__uint_as_float(s[cc + 2 * e2 + e]), p.scale_log2, -L[c]));
+              dsv = pr * (__uint_as_float(g[cc + 2 * e2 + e]) - Dd[c]) * p.scale;
             }
             a2[e] = pr;
             b2[e] = dsv;
@@ -494,10 +550,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) {
-        mbar_arrive(sdp_empty);
-        mbar_arrive(pt_full);
-      }
+      if (lane_id() == 0) mbar_arrive(pt_full);
     }
     mbar_wait(out_full, 0);
     tc_fence_after();

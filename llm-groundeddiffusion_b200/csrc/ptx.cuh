@@ -210,6 +210,13 @@ __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t xh2) {
   return y;
 }
 
+// three-input maximum (FMNMX3 on sm_100): halves the instruction count of a running row maximum
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
 // explicit shared-space 16-byte accesses (the compiler otherwise falls back to generic ST.E / LD.E for pointers it
 // derives from the dynamic shared-memory base)
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {

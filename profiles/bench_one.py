@@ -42,6 +42,14 @@ elif case == "attn":
     k[:, :, d:] = 0
     for _ in range(3):
         ops.attention_fwd(q, k, vt, B, heads, n, n, d, d ** -0.5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.attention_fwd(q, k, vt, B, heads, n, n, d, d ** -0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print("attn d=40 n=4096 B=16 ms", ms, "TF/s", 4.0 * n * n * d * heads * B / ms / 1e9)
 elif case == "qkv320":
     B, heads, d, n, C = 16, 8, 40, 4096, 320
     x, w = torch.randn(B * n, C, device=dev).half(), torch.randn(3 * C, C, device=dev).half()
