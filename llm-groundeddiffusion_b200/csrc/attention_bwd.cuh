@@ -163,12 +163,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int j = it - first_b;  // tile index inside pass B
       const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
       const uint32_t nphase = (nstage == 0) ? (phase ^ 1) : phase;
-      if (it + 1 < total) {
-        mbar_wait(&kv_full[nstage], nphase);
-        mbar_wait(sdp_empty, it & 1);
-        tc_fence_after();
-        issue_sdp(it + 1, nstage);
-      }
+      auto next_sdp = [&]() {
+        if (it + 1 < total) {
+          mbar_wait(&kv_full[nstage], nphase);
+          mbar_wait(sdp_empty, it & 1);
+          tc_fence_after();
+          issue_sdp(it + 1, nstage);
+        }
+      };
+      if constexpr (STAGES >= 2) next_sdp();   // with a single stage the next tile only lands after dQ(it) frees it
       const uint32_t ktaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES) + 2 * Cfg::K_BYTES;
       if (pass_b) {
         mbar_wait(ds_full, j & 1);
@@ -187,6 +190,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
       }
+      if constexpr (STAGES < 2) next_sdp();
       stage = nstage;
       phase = nphase;
     }
@@ -450,12 +454,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     for (int i = 0; i < nqt; ++i) {
       const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
       const uint32_t nphase = (nstage == 0) ? (phase ^ 1) : phase;
-      if (i + 1 < nqt) {
-        mbar_wait(&q_full[nstage], nphase);
-        mbar_wait(sdp_empty, i & 1);
-        tc_fence_after();
-        issue_sdp(nstage);
-      }
+      auto next_sdp = [&]() {
+        if (i + 1 < nqt) {
+          mbar_wait(&q_full[nstage], nphase);
+          mbar_wait(sdp_empty, i & 1);
+          tc_fence_after();
+          issue_sdp(nstage);
+        }
+      };
+      if constexpr (STAGES >= 2) next_sdp();   // with a single stage the next tile only lands after dV/dK(i) free it
       const uint32_t qtaddr = smem_u32(sStage + stage * Cfg::STAGE_BYTES) + 2 * Cfg::Q_BYTES;
       const uint32_t otaddr = qtaddr + Cfg::T_BYTES;
       mbar_wait(pt_full, i & 1);
@@ -478,6 +485,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         if (i == nqt - 1) tc_commit(out_full);
       }
       __syncwarp();
+      if constexpr (STAGES < 2) next_sdp();
       stage = nstage;
       phase = nphase;
     }

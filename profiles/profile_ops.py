@@ -41,7 +41,12 @@ class LibProxy:
     def __getattr__(self, name):
         if name not in self._cache:
             f = getattr(self._lib, name)
-            self._cache[name] = self._rec.wrap(f, lambda *a, _n=name, **k: (_n,)) if name.startswith("b200lmd_") and name not in ("b200lmd_gemm", "b200lmd_round_dp", "b200lmd_round_d16") else f
+            def keyfn(*a, _n=name, **k):
+                if "attention" in _n or "xattn" in _n:     # shape ints (B, heads, nq, nk, ..., d) tell the calls apart
+                    import ctypes
+                    return (_n,) + tuple(x.value for x in a if isinstance(x, ctypes.c_int))
+                return (_n,)
+            self._cache[name] = self._rec.wrap(f, keyfn) if name.startswith("b200lmd_") and name not in ("b200lmd_gemm", "b200lmd_round_dp", "b200lmd_round_d16") else f
         return self._cache[name]
 
 
