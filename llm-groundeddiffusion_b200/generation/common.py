@@ -112,7 +112,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
                       so_vertical_placement, so_floor_padding, fg_blending_ratio, align_with_overall_bboxes,
                       horizontal_shift_only, use_ref_ca, ref_ca_loss_weight, so_negative_prompt, overall_negative_prompt,
                       guidance_scale=7.5, height=512, width=512, keys=None, overall_prompt_overrides=None,
-                      return_latents=False):
+                      return_latents=False, use_fast_schedule=False):
     """Two-phase generation for a batch of specs.  so_guidance / overall_guidance: dict(loss_scale, loss_threshold,
     max_iter, max_index_step, fg_top_p, bg_top_p, fg_weight, bg_weight) or None."""
     net, env = _need()
@@ -120,6 +120,12 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
     H, W = height // 8, width // 8
     steps = num_inference_steps
     frozen_steps = int(steps * min(max(frozen_step_ratio, 0.0), 1.0))
+    # generation/lmd_plus.py:360-367: the per-box generations only need the steps whose latents / attention are
+    # transferred; after those the timestep list is thinned (the result only feeds the mask refinement)
+    fast_after_steps = None
+    if use_fast_schedule:
+        ov_mis = overall_guidance["max_index_step"] if overall_guidance is not None else 0
+        fast_after_steps = max(frozen_steps, ov_mis) if use_ref_ca else frozen_steps
     B = len(specs)
     conv = [convert_spec(s, height, width) for s in specs]
     so_lists, overall_prompts, overall_pwb = [c[0] for c in conv], [c[1] for c in conv], [c[2] for c in conv]
@@ -163,7 +169,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
         resA = P.denoise(net, torch.cat(z_list, 0), torch.cat(unc_list, 0), torch.cat(cond_list, 0), steps,
                          guidance_scale=guidance_scale, guidance=gspec, gligen=gl, gligen_beta=so_beta,
                          save_keys=[("down", 2, 1, 0)] + (keys if use_ref_ca else []), save_tok=tok_list,
-                         save_latents=True)
+                         save_latents=True, fast_after_steps=fast_after_steps, dynamic_num_inference_steps=True)
         imgs = env.decode(resA["latents"])
         la = resA["latents_all"].cpu()                         # [steps+1, BA, C, H, W]
         for i in range(len(owner)):
@@ -186,7 +192,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
         offsets = [(0.0, 0.0)] * len(idx)
         if align_with_overall_bboxes and lat_b:
             lat_b, msk_b, offsets = L.align_to_boxes(lat_b, msk_b, flat, horizontal_only=horizontal_shift_only)
-        comp, fg_idx = L.compose(lat_b, msk_b, bg_latents[b], steps)
+        comp, fg_idx = L.compose(lat_b, msk_b, bg_latents[b], steps if fast_after_steps is None else fast_after_steps)
         composed.append(comp)
         frozen_masks.append((fg_idx != 0).float())
         pos, widx, prompt = env.phrase_indices(overall_prompts[b], phrases, words, add_suffix=True)

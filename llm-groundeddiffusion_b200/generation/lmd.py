@@ -18,8 +18,6 @@ def run_batch(specs, bg_seeds, fg_seed_starts, overall_prompt_overrides=None, fr
               so_horizontal_center_only=False, align_with_overall_bboxes=True, horizontal_shift_only=False,
               use_fast_schedule=False, so_vertical_placement="floor_padding", so_floor_padding=0.2, use_box_input=False,
               use_ref_ca=True, use_autocast=False, verbose=False, return_latents=False):
-    if use_fast_schedule:
-        raise NotImplementedError("use_fast_schedule (utils/schedule.py:4-8) is not built yet")
     so_g = dict(loss_scale=loss_scale, loss_threshold=loss_threshold, max_iter=max_iter, max_index_step=max_index_step,
                 fg_top_p=fg_top_p, bg_top_p=bg_top_p, fg_weight=fg_weight, bg_weight=bg_weight)
     ov_g = dict(loss_scale=overall_loss_scale, loss_threshold=overall_loss_threshold, max_iter=overall_max_iter,
@@ -33,7 +31,7 @@ def run_batch(specs, bg_seeds, fg_seed_starts, overall_prompt_overrides=None, fr
         fg_blending_ratio=fg_blending_ratio, align_with_overall_bboxes=align_with_overall_bboxes,
         horizontal_shift_only=horizontal_shift_only, use_ref_ca=use_ref_ca, ref_ca_loss_weight=ref_ca_loss_weight,
         so_negative_prompt=so_negative_prompt, overall_negative_prompt=overall_negative_prompt,
-        overall_prompt_overrides=overall_prompt_overrides, return_latents=return_latents)
+        overall_prompt_overrides=overall_prompt_overrides, return_latents=return_latents, use_fast_schedule=use_fast_schedule)
 
 
 def run(spec, bg_seed=1, overall_prompt_override="", fg_seed_start=20, **kwargs):

@@ -17,8 +17,6 @@ def run_batch(specs, bg_seeds, fg_seed_starts, overall_prompt_overrides=None, fr
               overall_negative_prompt=DEFAULT_OVERALL_NEGATIVE_PROMPT, so_horizontal_center_only=True,
               align_with_overall_bboxes=False, horizontal_shift_only=True, use_fast_schedule=False, use_ref_ca=True,
               use_autocast=True, verbose=False, return_latents=False):
-    if use_fast_schedule:
-        raise NotImplementedError("use_fast_schedule (utils/schedule.py:4-8) is not built yet")
     so_g = dict(loss_scale=loss_scale, loss_threshold=loss_threshold, max_iter=max_iter, max_index_step=max_index_step)
     ov_g = dict(loss_scale=overall_loss_scale, loss_threshold=overall_loss_threshold, max_iter=overall_max_iter,
                 max_index_step=overall_max_index_step, fg_top_p=overall_fg_top_p, bg_top_p=overall_bg_top_p,
@@ -32,7 +30,7 @@ def run_batch(specs, bg_seeds, fg_seed_starts, overall_prompt_overrides=None, fr
         align_with_overall_bboxes=align_with_overall_bboxes, horizontal_shift_only=horizontal_shift_only,
         use_ref_ca=use_ref_ca, ref_ca_loss_weight=ref_ca_loss_weight, so_negative_prompt=so_negative_prompt,
         overall_negative_prompt=overall_negative_prompt, overall_prompt_overrides=overall_prompt_overrides,
-        return_latents=return_latents)
+        return_latents=return_latents, use_fast_schedule=use_fast_schedule)
 
 
 def run(spec, bg_seed=1, overall_prompt_override="", fg_seed_start=20, **kwargs):

@@ -47,6 +47,20 @@ class DDIMSchedule:
         self.num_inference_steps = n
         self.timesteps = (np.arange(0, n) * (1000 // n)).round()[::-1].astype(np.int64) + 1
 
+    def apply_fast_schedule(self, fast_after_steps, fast_rate=2):
+        """utils/schedule.py:4-9 get_fast_schedule: keep the first `fast_after_steps` timesteps, then every
+        `fast_rate`-th of the rest (starting one past the cut)."""
+        ts = self.timesteps
+        if fast_after_steps >= len(ts) - 1:
+            return
+        self.timesteps = np.concatenate([ts[:fast_after_steps], ts[fast_after_steps + 1::fast_rate]])
+
+    def adjust(self, index, t):
+        """utils/schedule.py:11-19 dynamically_adjust_inference_steps: the DDIM step lands on the next listed timestep
+        (prev_timestep = t - 1000 // num_inference_steps), -1 past the end."""
+        prev_t = int(self.timesteps[index + 1]) if index + 1 < len(self.timesteps) else -1
+        self.num_inference_steps = 1000 // (int(t) - prev_t)
+
     def coefs(self, t):
         prev_t = int(t) - 1000 // self.num_inference_steps
         a_t = float(self.alphas_cumprod[int(t)])
@@ -188,17 +202,23 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
 
 def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional[GuidanceSpec] = None,
             frozen_mask=None, frozen_latents=None, frozen_steps=0, gligen=None, gligen_beta=0.3, save_keys=None,
-            save_tok: Optional[Sequence[int]] = None, save_latents=False, prediction_type="epsilon", use_graphs=True):
+            save_tok: Optional[Sequence[int]] = None, save_latents=False, prediction_type="epsilon", use_graphs=True,
+            fast_after_steps=None, fast_rate=2, dynamic_num_inference_steps=False):
     """B images in lock-step.  z0 [B,4,H,W] fp32 (any device); uncond [1 or B,T,ctx]; cond [B,T,ctx];
     frozen_mask [B,H,W] or [H,W] (1 = take the frozen latent), frozen_latents [steps+1,B,4,H,W];
     gligen: dict(boxes [B,30,4], masks [B,30], positive_embeddings [B,30,768]) of the conditional half;
     save_keys/save_tok: per step keep the cond-half map column tok[b] of those keys (return_cond_ca_only +
-    return_token_ca_only).  Returns dict(latents, latents_all, saved, state)."""
+    return_token_ca_only).  fast_after_steps / fast_rate / dynamic_num_inference_steps: the reference's fast schedule
+    (models/pipelines.py:358-362,439-440,449): thinned timestep list after `fast_after_steps`, DDIM step size
+    re-derived per step, latents kept only for index < fast_after_steps.
+    Returns dict(latents, latents_all, saved, state)."""
     dev = net.dev
     z = z0.to(dev, torch.float32).contiguous().clone()
     B, Cz, H, W = z.shape
     sched = DDIMSchedule(prediction_type)
     sched.set_timesteps(steps)
+    if fast_after_steps is not None:
+        sched.apply_fast_schedule(fast_after_steps, fast_rate)
     if uncond.shape[0] == 1:
         uncond = uncond.expand(B, -1, -1)
     text = torch.cat([uncond, cond], dim=0)
@@ -206,7 +226,7 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
     heads_of = lambda p: kv.slabs[p][0].shape[0] // (2 * B)
     kv_cond = lambda p: tuple(s[B * heads_of(p):] for s in kv.slabs[p])
     objs_main = objs_guid = None
-    n_ground = int(gligen_beta * steps)
+    n_ground = int(gligen_beta * len(sched.timesteps))       # models/pipelines.py:408
     if gligen is not None:
         rep2 = lambda x: torch.cat([x, x], dim=0)
         masks2 = rep2(gligen["masks"]).clone()
@@ -244,6 +264,8 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
                                      save_tok=tok_dev)
         if save_keys is not None:       # graph outputs are static buffers: keep a copy of this step's maps
             saved_all.append({k: v["tok"][B:].clone() for k, v in saved.items()})
+        if dynamic_num_inference_steps:
+            sched.adjust(index, t)
         sa_t, sb_t, sa_p, sb_p = sched.coefs(t)
         use_frozen = fm is not None and index < frozen_steps
         check(lib().b200lmd_cfg_ddim_blend(ptr(z), ptr(eps), _i(eps.shape[3]), _i(B), _i(Cz), _i(H * W),
@@ -251,7 +273,7 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
                                            _i(int(prediction_type == "v_prediction")),
                                            ptr(fl[index + 1]) if use_frozen else None, ptr(fm) if use_frozen else None,
                                            cur_stream()))
-        if save_latents:
+        if save_latents and (fast_after_steps is None or index < fast_after_steps):
             latents_all.append(z.clone())
     return dict(latents=z, latents_all=torch.stack(latents_all, 0) if save_latents else None, saved=saved_all,
                 state=state)

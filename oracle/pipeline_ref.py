@@ -30,6 +30,18 @@ class DDIM:
         ratio = 1000 // n
         self.timesteps = (np.arange(0, n) * ratio).round()[::-1].astype(np.int64) + 1
 
+    def apply_fast_schedule(self, fast_after_steps, fast_rate=2):
+        """utils/schedule.py:4-9"""
+        ts = self.timesteps
+        if fast_after_steps >= len(ts) - 1:
+            return
+        self.timesteps = np.concatenate([ts[:fast_after_steps], ts[fast_after_steps + 1::fast_rate]])
+
+    def adjust(self, index, t):
+        """utils/schedule.py:11-13 (the warnings of :14-19 do not change results)"""
+        prev_t = int(self.timesteps[index + 1]) if index + 1 < len(self.timesteps) else -1
+        self.num_inference_steps = 1000 // (int(t) - prev_t)
+
     def step(self, eps_or_v, t, x):
         prev_t = int(t) - 1000 // self.num_inference_steps
         a_t = self.alphas_cumprod[int(t)]
@@ -93,7 +105,8 @@ def guidance_iterations(unet: Callable, sched: DDIM, z, t, index, loss, g: Guida
 
 def denoise(w, cfg: unet_ref.UNetConfig, z0, uncond, cond, steps, guidance_scale=7.5, g: Optional[GuidanceCfg] = None,
             frozen_mask=None, frozen_latents=None, frozen_steps=0, gligen=None, gligen_beta=0.3,
-            save_keys=None, save_token=None, prediction_type="epsilon", trace=None):
+            save_keys=None, save_token=None, prediction_type="epsilon", trace=None, fast_after_steps=None,
+            fast_rate=2, dynamic_num_inference_steps=False):
     """z0 [1,4,H,W]; uncond/cond [1,T,ctx].  Returns dict(latents, latents_all [steps+1], saved (per step), iters).
     gligen: dict(boxes [1,30,4], masks [1,30], positive_embeddings [1,30,768]) for the conditional half.
     Reference quirks reproduced: CFG batch order [uncond; cond] (pipelines.py:420, models.py:85); the guidance pass
@@ -101,13 +114,15 @@ def denoise(w, cfg: unet_ref.UNetConfig, z0, uncond, cond, steps, guidance_scale
     index < int(beta*steps) (pipelines.py:408-414); frozen blend uses latents_all_input[index+1] (pipelines.py:446)."""
     sched = DDIM(prediction_type)
     sched.set_timesteps(steps)
+    if fast_after_steps is not None:                    # pipelines.py:151-152, 358-359
+        sched.apply_fast_schedule(fast_after_steps, fast_rate)
     z = z0.clone()
     latents_all = [z.clone()]
     saved_all = []
     iters = []
     loss = 10000.0
     text = torch.cat([uncond, cond], dim=0)
-    n_ground = int(gligen_beta * steps)
+    n_ground = int(gligen_beta * len(sched.timesteps))  # pipelines.py:408
     gl_main = gl_guid = None
     if gligen is not None:
         rep = lambda x: torch.cat([x, x], dim=0)
@@ -135,8 +150,11 @@ def denoise(w, cfg: unet_ref.UNetConfig, z0, uncond, cond, steps, guidance_scale
                 saved_all.append({k: (v[1:, :, :, save_token:save_token + 1] if save_token is not None else v[1:])
                                   for k, v in saved.items()})
             eps = eps[:1] + guidance_scale * (eps[1:] - eps[:1])
+            if dynamic_num_inference_steps:             # pipelines.py:217-218, 439-440
+                sched.adjust(index, t)
             z = sched.step(eps, t, z)
             if frozen_mask is not None and index < frozen_steps:
                 z = frozen_latents[index + 1] * frozen_mask + z * (1.0 - frozen_mask)
-        latents_all.append(z.clone())
+        if fast_after_steps is None or index < fast_after_steps:   # pipelines.py:449
+            latents_all.append(z.clone())
     return dict(latents=z, latents_all=torch.stack(latents_all, 0), saved=saved_all, iters=iters, loss=loss)

@@ -1,6 +1,8 @@
 """DDIMScheduler as published in diffusers 0.18.0 schedulers/scheduling_ddim.py (restated; eta=0 path)."""
 from dataclasses import dataclass
 
+import types
+
 import numpy as np
 import torch
 
@@ -16,6 +18,8 @@ class DDIMScheduler:
                  clip_sample=False, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon"):
         assert beta_schedule == "scaled_linear"
         self.num_train_timesteps = num_train_timesteps
+        self.config = types.SimpleNamespace(num_train_timesteps=num_train_timesteps, prediction_type=prediction_type,
+                                            steps_offset=steps_offset)   # utils/schedule.py:12 reads scheduler.config
         self.betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)

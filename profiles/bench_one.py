@@ -63,5 +63,25 @@ elif case == "qkv320":
     e1.record()
     torch.cuda.synchronize()
     print("qkv320 ms", e0.elapsed_time(e1) / 10)
+elif case == "attn_bwd":
+    B, heads, d, n = 8, 8, 40, 4096
+    dp, d16 = ops.round_dp(d), ops.round_d16(d)
+    rm = lambda: torch.randn(B * heads, n, dp, device=dev).half()
+    tr = lambda: torch.randn(B * heads, d16, n, device=dev).half()
+    q, k, v, dO, qt, kt, dOt = rm(), rm(), rm(), rm(), tr(), tr(), tr()
+    for t in (q, k, v, dO):
+        t[:, :, d:] = 0
+    vt = v[:, :, :d16].transpose(1, 2).contiguous()
+    out, lse = ops.attention_fwd(q, k, vt, B, heads, n, n, d, d ** -0.5, want_lse=True)
+    do_tok = torch.randn(B * n, heads * d, device=dev).half()
+    for _ in range(2):
+        ops.attention_bwd(q, k, v, dO, qt, kt, dOt, lse, out, do_tok, B, heads, n, n, d, d ** -0.5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.attention_bwd(q, k, v, dO, qt, kt, dOt, lse, out, do_tok, B, heads, n, n, d, d ** -0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    print("attn_bwd d=40 n=4096 B=8 ms", e0.elapsed_time(e1) / 5)
 torch.cuda.synchronize()
 print("done", case)

@@ -143,3 +143,22 @@ def test_convert_spec_and_synthetic_env():
     assert p3 == "a room| a bird" and env.tokens(p3)[widx[0]] == "bird"
     u, c = env.encode_prompts(["x", "y"], "neg")
     assert u.shape == (1, 77, 768) and c.shape == (2, 77, 768) and not torch.equal(c[0], c[1])
+
+
+def test_fast_schedule_host_logic():
+    """utils/schedule.py:4-19 semantics on the host scheduler (known-answer: 10 steps, cut after 5, every 2nd)"""
+    from lgd_b200.pipelines import DDIMSchedule
+    s = DDIMSchedule()
+    s.set_timesteps(10)
+    assert s.timesteps.tolist() == [901, 801, 701, 601, 501, 401, 301, 201, 101, 1]
+    s.apply_fast_schedule(5, 2)
+    assert s.timesteps.tolist() == [901, 801, 701, 601, 501, 301, 101]
+    nis = []
+    for i, t in enumerate(s.timesteps.tolist()):
+        s.adjust(i, t)
+        nis.append(s.num_inference_steps)
+    assert nis == [10, 10, 10, 10, 5, 5, 9]          # 1000 // (t - next t), last: 1000 // (101 + 1)
+    s2 = DDIMSchedule()
+    s2.set_timesteps(10)
+    s2.apply_fast_schedule(9, 2)                     # cut at or past the end: unchanged
+    assert len(s2.timesteps) == 10

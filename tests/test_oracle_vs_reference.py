@@ -190,3 +190,59 @@ def test_gligen_loop_with_ref_attention_matches_reference():
                                gligen=dict(boxes=boxes, masks=masks, positive_embeddings=emb), gligen_beta=0.5)
     assert res["iters"] == [2, 1, 1, 0]
     assert (res["latents"] - lat_ref).abs().max() < 5e-3
+
+
+def test_gligen_loop_fast_schedule_matches_reference():
+    """generate_gligen with the thinned timestep list and per-step DDIM step size (fast_after_steps, fast_rate,
+    dynamic_num_inference_steps; models/pipelines.py:358-362,439-440)"""
+    cfg, w, r, md, z0, uncond, cond, table = _setup_pipeline(True)
+    steps = 8
+    bboxes_flat = [(0.1, 0.2, 0.6, 0.7)]
+    lat_ref, _ = r.pipelines.generate_gligen(
+        md, z0, (uncond, cond), steps, bboxes_flat, ["a cat"], gligen_scheduled_sampling_beta=0.5,
+        semantic_guidance=False, show_progress=False, fast_after_steps=3, fast_rate=2, dynamic_num_inference_steps=True)
+    boxes = torch.zeros(1, 30, 4)
+    boxes[0, :1] = torch.tensor(bboxes_flat)
+    emb = torch.zeros(1, 30, 768)
+    emb[0, :1] = table[:1]
+    masks = torch.zeros(1, 30)
+    masks[0, :1] = 1
+    res = pipeline_ref.denoise(w, cfg, z0, uncond, cond, steps, gligen=dict(boxes=boxes, masks=masks,
+                                                                           positive_embeddings=emb),
+                               gligen_beta=0.5, fast_after_steps=3, fast_rate=2, dynamic_num_inference_steps=True)
+    assert res["latents_all"].shape[0] == 4            # initial + the three steps before the fast part
+    assert (res["latents"] - lat_ref).abs().max() < 5e-3
+
+
+def test_fast_schedule_matches_reference():
+    """utils/schedule.py (get_fast_schedule, dynamically_adjust_inference_steps) vs pipelines.DDIMSchedule"""
+    import lgd_b200  # noqa: F401
+    from lgd_b200.pipelines import DDIMSchedule
+    r = ref_loader.load()
+    import importlib
+    ref_sched = importlib.import_module("utils.schedule")
+
+    class _Cfg:
+        num_train_timesteps = 1000
+
+    class _S:
+        config = _Cfg()
+
+    for steps in (10, 20, 50):
+        for fast_after in (0, 3, steps // 2, steps - 2, steps - 1, steps + 5):
+            for rate in (2, 3):
+                ours = DDIMSchedule()
+                ours.set_timesteps(steps)
+                ref_ts = ref_sched.get_fast_schedule(torch.from_numpy(ours.timesteps.copy()), fast_after, rate)
+                ours.apply_fast_schedule(fast_after, rate)
+                assert ours.timesteps.tolist() == ref_ts.tolist()
+                s = _S()
+                s.timesteps = ref_ts
+                for index, t in enumerate(ref_ts.tolist()):
+                    import warnings
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        ref_sched.dynamically_adjust_inference_steps(s, index, t)
+                    ours.adjust(index, t)
+                    assert ours.num_inference_steps == s.num_inference_steps
+    assert r is not None

@@ -104,3 +104,29 @@ def test_gligen_ref_frozen_loop(cuda):
         # fp16 and fp32 maps (the autocast reference has the same sensitivity), so the bound is loose
         assert r < 0.15, r
         assert abs(res["state"].loss[b] - ref["loss"]) < 0.15 * abs(ref["loss"])
+
+
+def test_fast_schedule_loop(cuda):
+    """thinned timestep list + per-step DDIM step size (use_fast_schedule of generation/lmd_plus.py:360-367,
+    models/pipelines.py:358-362,439-440,449) vs the oracle loop"""
+    from lgd_b200 import pipelines as P
+    from oracle import pipeline_ref
+    B, steps = 2, 8
+    ocfg, w, net, g, z0, uncond, cond = _common(True, B)
+    gl = dict(boxes=torch.zeros(B, 30, 4), masks=torch.zeros(B, 30), positive_embeddings=torch.zeros(B, 30, 768))
+    for b in range(B):
+        gl["boxes"][b, 0] = torch.tensor([0.1 + 0.2 * b, 0.2, 0.6 + 0.2 * b, 0.7])
+        gl["masks"][b, 0] = 1
+        gl["positive_embeddings"][b, 0] = torch.randn(768, generator=g)
+    res = P.denoise(net, z0, uncond, cond, steps, gligen=gl, gligen_beta=0.5, save_latents=True, fast_after_steps=3,
+                    fast_rate=2, dynamic_num_inference_steps=True)
+    torch.cuda.synchronize()
+    assert res["latents_all"].shape[0] == 4
+    for b in range(B):
+        ref = pipeline_ref.denoise(w, ocfg, z0[b:b + 1], uncond, cond[b:b + 1], steps,
+                                   gligen={k: v[b:b + 1] for k, v in gl.items()}, gligen_beta=0.5, fast_after_steps=3,
+                                   fast_rate=2, dynamic_num_inference_steps=True)
+        r = _rel(res["latents"][b:b + 1].cpu(), ref["latents"])
+        print("image", b, "final-latent rel-L2", r)
+        assert r < 2e-2, r
+        assert _rel(res["latents_all"][:, b:b + 1].cpu(), ref["latents_all"]) < 2e-2
