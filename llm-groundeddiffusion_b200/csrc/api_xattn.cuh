@@ -83,16 +83,17 @@ inline unsigned long long*& fused_dbg() {
   static unsigned long long* p = nullptr;
   return p;
 }
-// zeroed per launch (stream-ordered memset, graph-capturable); grown on demand outside of capture
+// hand-shake counters: zero when allocated, and the kernel leaves them at zero (the last arriver of every counter
+// resets it), so no memset sits between launches; grown on demand outside of capture
 inline int* fused_flags(int n_ints, cudaStream_t st) {
   static int* buf = nullptr;
   static int cap = 0;
   if (n_ints > cap) {
     if (buf) cudaFree(buf);
-    cap = n_ints < 8192 ? 8192 : n_ints;
+    cap = n_ints < 16384 ? 16384 : n_ints;
     B200_CHECK(cudaMalloc(&buf, sizeof(int) * cap));
+    B200_CHECK(cudaMemsetAsync(buf, 0, sizeof(int) * cap, st));
   }
-  B200_CHECK(cudaMemsetAsync(buf, 0, sizeof(int) * n_ints, st));
   return buf;
 }
 // per (image, head, row tile) loss partials; never needs zeroing
@@ -161,8 +162,9 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     p.dbg = fused_dbg();
     // per-row-tile arrival counters live right behind the scratch rows of o_scratch's owner: a small static buffer
     const int n_tiles = (int)(M / 128);
-    p.tile_flags = fused_flags(n_tiles + 2 * B * 8, (cudaStream_t)stream);
-    p.bh_ready = p.tile_flags + n_tiles;
+    p.tile_flags = fused_flags(2 * n_tiles + 2 * B * 8, (cudaStream_t)stream);
+    p.tile_done = p.tile_flags + n_tiles;
+    p.bh_ready = p.tile_done + n_tiles;
     p.bh_done = p.bh_ready + B * 8;
     p.loss_partials = fused_partials(n_tiles * 8);
     CUtensorMap tmX = rowmajor_map_2d((const __half*)x, M, C, C, 32);

@@ -497,15 +497,25 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int krow = kt * 128 + r;
     const bool kok = krow < p.nk;
+    // row statistic / delta of the query tile: double-buffered in shared memory, the next tile's values are fetched
+    // (global loads in flight) while this tile is processed
+    if (tid < QT) {
+      sL[tid] = tid < p.nq ? p.lse2[(long long)bh * p.nq_alloc + tid] : 0.f;
+      sD[tid] = tid < p.nq ? p.delta[(long long)bh * p.nq_alloc + tid] : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = 0; i < nqt; ++i) {
-      float* L = sL + (i & 1) * QT;
-      float* Dd = sD + (i & 1) * QT;
-      if (tid < QT) {
-        const int q = i * QT + tid;
-        L[tid] = q < p.nq ? p.lse2[(long long)bh * p.nq_alloc + q] : 0.f;
-        Dd[tid] = q < p.nq ? p.delta[(long long)bh * p.nq_alloc + q] : 0.f;
+      const float* L = sL + (i & 1) * QT;
+      const float* Dd = sD + (i & 1) * QT;
+      const bool pf = (i + 1 < nqt) && (tid < QT);
+      float nl = 0.f, nd = 0.f;
+      if (pf) {
+        const int q = (i + 1) * QT + tid;
+        if (q < p.nq) {
+          nl = p.lse2[(long long)bh * p.nq_alloc + q];
+          nd = p.delta[(long long)bh * p.nq_alloc + q];
+        }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
       // this warp's half of the S^T / dP^T rows into registers, then TMEM is free for the next query tile's MMAs
@@ -528,21 +538,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const int c0 = cb + cc;
         uint32_t pp[16], ds[16];
 #pragma unroll
-        for (int e2 = 0; e2 < 16; ++e2) {
-          float a2[2], b2[2];
+        for (int e4 = 0; e4 < 8; ++e4) {       // four query columns per step: one 16-byte read of each table
+          const float4 l4 = *reinterpret_cast<const float4*>(L + c0 + 4 * e4);
+          const float4 d4 = *reinterpret_cast<const float4*>(Dd + c0 + 4 * e4);
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pr[4], dsv[4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = c0 + 2 * e2 + e;
-            float pr = 0.f, dsv = 0.f;
-            if (full || (kok && (i * QT + c) < p.nq)) {
-              pr = ex2_approx(fmaf(__uint_as_float(s[cc + 2 * e2 + e]), p.scale_log2, -L[c]));
-              dsv = pr * (__uint_as_float(g[cc + 2 * e2 + e]) - Dd[c]) * p.scale;
-            }
-            a2[e] = pr;
-            b2[e] = dsv;
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + 4 * e4 + e;
+            const float pe = ex2_approx(fmaf(__uint_as_float(s[cc + 4 * e4 + e]), p.scale_log2, -lv[e]));
+            const float de = pe * (__uint_as_float(g[cc + 4 * e4 + e]) - dv[e]) * p.scale;
+            const bool valid = full || (kok && (i * QT + c) < p.nq);   // ragged edges: select, no branch
+            pr[e] = valid ? pe : 0.f;
+            dsv[e] = valid ? de : 0.f;
           }
-          pp[e2] = pack_h2(a2[0], a2[1]);
-          ds[e2] = pack_h2(b2[0], b2[1]);
+          pp[2 * e4] = pack_h2(pr[0], pr[1]);
+          pp[2 * e4 + 1] = pack_h2(pr[2], pr[3]);
+          ds[2 * e4] = pack_h2(dsv[0], dsv[1]);
+          ds[2 * e4 + 1] = pack_h2(dsv[2], dsv[3]);
         }
         const int ch0 = (c0 & 63) >> 3;
         uint8_t* pa = sPT + (c0 >> 6) * 16384;
@@ -559,6 +572,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(pt_full);
+      if (pf) {
+        sL[((i + 1) & 1) * QT + tid] = nl;
+        sD[((i + 1) & 1) * QT + tid] = nd;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // next tile's tables visible; this tile's reads are done
     }
     mbar_wait(out_full, 0);
     tc_fence_after();

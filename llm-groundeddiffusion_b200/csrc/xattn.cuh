@@ -346,10 +346,10 @@ __device__ __forceinline__ void loss_zero(const XattnLoss& L, int bh, int n, int
 #define LOSS_STAMP(i) do { if (dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = t_; } } while (0)
 // part/nparts: the problems are dealt round-robin to nparts CTAs x 4 warps.  With nparts > 1 every CTA leaves its
 // partial in partials[bh*nparts + part] and the last one to arrive (done[bh]) adds them up in part order, so the sum
-// does not depend on arrival order.  done[bh] must be zero on entry.
+// does not depend on arrival order.  done[bh] must be zero on entry and is zero again on exit (so is ready[bh]).
 __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int tid, int h, int heads, int bh, int n,
                                          int part, int nparts, float* partials, int* done,
-                                         unsigned long long* dbg = nullptr) {
+                                         unsigned long long* dbg = nullptr, int* ready = nullptr) {
   const int warp = tid >> 5, lane = tid & 31;
   LossScratch S = loss_scratch(scratch);
   const int n_prob = *S.n_prob;
@@ -370,6 +370,7 @@ __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int
       if (((i >> 2) % nparts) == part) acc += S.prob_loss[i];
     if (nparts == 1) {
       L.loss_part[bh] = acc;
+      if (ready) ready[bh] = 0;                            // hand-shake counters end the launch at zero
     } else {
       __stcg(partials + bh * nparts + part, acc);
       __threadfence();
@@ -378,6 +379,8 @@ __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int
         float tot = 0.f;
         for (int q = 0; q < nparts; ++q) tot += __ldcg(partials + bh * nparts + q);
         L.loss_part[bh] = tot;
+        done[bh] = 0;                                      // every part is past its wait on `ready` by now
+        if (ready) ready[bh] = 0;
       }
     }
   }

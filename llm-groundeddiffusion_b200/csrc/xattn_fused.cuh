@@ -33,6 +33,7 @@ struct FusedXattnParams {
   int has_loss;
   XattnLoss L;
   int* tile_flags;           // [row tiles] zero on entry: counts the heads of a row tile whose O_h is published
+  int* tile_done;            // [row tiles] zero on entry: heads that have seen the full count; the last one re-zeroes both
   int* bh_ready;             // [B*8] zero on entry: row tiles of an (image, head) whose P columns are published
   int* bh_done;              // [B*8] zero on entry: row tiles of an (image, head) that finished their loss share
   float* loss_partials;      // [B*8][tiles_per_img]
@@ -396,6 +397,11 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         __nanosleep(64);
       }
       __threadfence();
+      // every flag is back to zero when the kernel ends (no memset between launches): the last head to get here resets
+      if (atomicAdd(&p.tile_done[rt], 1) == 7) {
+        p.tile_flags[rt] = 0;
+        p.tile_done[rt] = 0;
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
@@ -470,7 +476,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       loss_run(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, p.loss_partials, p.bh_done,
-               p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr);
+               p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr, p.bh_ready);
     }
     if (p.residual) {
       asm volatile("cp.async.wait_all;" ::: "memory");

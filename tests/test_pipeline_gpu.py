@@ -130,3 +130,38 @@ def test_fast_schedule_loop(cuda):
         print("image", b, "final-latent rel-L2", r)
         assert r < 2e-2, r
         assert _rel(res["latents_all"][:, b:b + 1].cpu(), ref["latents_all"]) < 2e-2
+
+
+def test_v_prediction_guidance_loop(cuda):
+    """BASELINE config 3 semantics on a small topology: SD2.1-style UNet (head_dim 64, linear projections, 1024-wide
+    context), v-prediction DDIM step, backward-guidance constants (loss_scale 30, threshold 0.2, max_iter 5,
+    max_index_step 10 -> here 2)"""
+    from lgd_b200 import guidance as G, pipelines as P
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import pipeline_ref, unet_ref
+    kw = dict(block_out_channels=(128, 256, 512, 512), heads=(2, 4, 8, 8), cross_attention_dim=1024,
+              use_linear_projection=True)
+    ocfg = unet_ref.UNetConfig(**kw)
+    w = unet_ref.make_weights(ocfg, seed=2)
+    net = B200UNet(UNetConfig(**kw), w, "cuda:0")
+    B, steps, side = 2, 3, 32
+    g = torch.Generator().manual_seed(8)
+    z0 = torch.randn(B, 4, side, side, generator=g)
+    uncond = torch.randn(1, 77, 1024, generator=g)
+    cond = torch.randn(B, 77, 1024, generator=g)
+    lay = [G.SampleLayout([[(0.1, 0.2, 0.6, 0.7)]], [[2, 3]], [3]),
+           G.SampleLayout([[(0.4, 0.3, 0.9, 0.8)]], [[5]], [5])]
+    spec = P.GuidanceSpec(layouts=lay, keys=KEYS, loss_scale=3, loss_threshold=0.2, max_iter=2, max_index_step=2,
+                          fg_weight=1.0, bg_weight=1.0)
+    res = P.denoise(net, z0, uncond, cond, steps, guidance=spec, prediction_type="v_prediction")
+    torch.cuda.synchronize()
+    iters = list(zip(*res["state"].iters))
+    for b in range(B):
+        og = pipeline_ref.GuidanceCfg(lay[b].bboxes, lay[b].object_positions, KEYS, 3, 0.2, 2, 2, 0.2, 0.2, 1.0, 1.0)
+        ref = pipeline_ref.denoise(w, ocfg, z0[b:b + 1], uncond, cond[b:b + 1], steps, g=og,
+                                   prediction_type="v_prediction")
+        assert list(iters[b]) == ref["iters"], (iters[b], ref["iters"])
+        r = _rel(res["latents"][b:b + 1].cpu(), ref["latents"])
+        print("image", b, "final-latent rel-L2", r, "oracle loss", ref["loss"], "ours", res["state"].loss[b])
+        assert r < 0.15, r
+        assert abs(res["state"].loss[b] - ref["loss"]) < 0.15 * abs(ref["loss"])

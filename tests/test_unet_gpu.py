@@ -126,3 +126,31 @@ def test_guidance_gradient_fused_xattn_path(cuda):
     print("fused path: loss", float(grads[True][1][0]), float(L), "grad rel-L2", r)
     assert abs(float(grads[True][1][0]) - float(L)) < 2e-2 * abs(float(L))
     assert r < 8e-2, r
+
+
+def test_forward_sd21_style_matches_oracle(cuda):
+    """SD2.1-style topology (BASELINE config 3): per-level head counts with head_dim 64, Linear proj_in/proj_out
+    (transformer_2d.py:272-296), 1024-wide text context"""
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import unet_ref
+    kw = dict(block_out_channels=(128, 256, 512, 512), heads=(2, 4, 8, 8), cross_attention_dim=1024,
+              use_linear_projection=True)
+    ocfg = unet_ref.UNetConfig(**kw)
+    w = unet_ref.make_weights(ocfg, seed=5)
+    net = B200UNet(UNetConfig(**kw), w, "cuda:0")
+    B, side = 2, 24                       # 24x24 latents: 576 / 144 / 36 / 9 tokens (ragged tiles everywhere)
+    g = torch.Generator().manual_seed(6)
+    z = torch.randn(B, 4, side, side, generator=g)
+    text = torch.randn(2 * B, 77, 1024, generator=g)
+    kv = net.set_text(text)
+    t = torch.full((2 * B,), 301.0, device=cuda)
+    eps, saved = net.forward(z.to(cuda), t, kv, rep=2, save_keys=None, save_probs=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_saved = {}
+        ref = unet_ref.unet_forward(w, ocfg, torch.cat([z, z], 0), 301, text, saved=ref_saved)
+    r = _rel(eps.permute(0, 3, 1, 2).cpu(), ref)
+    print("eps rel-L2 (sd21-style)", r)
+    assert r < 2e-2, r
+    for k in ref_saved:
+        assert (saved[k]["probs"].float().cpu() - ref_saved[k]).abs().max() < 6e-2, k
