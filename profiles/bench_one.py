@@ -63,6 +63,27 @@ elif case == "qkv320":
     e1.record()
     torch.cuda.synchronize()
     print("qkv320 ms", e0.elapsed_time(e1) / 10)
+elif case in ("toout320", "geglu320"):
+    M, N, K = 65536, 320, 1280
+    if case == "geglu320":
+        N, K = 2560, 320
+    x, w = torch.randn(M, K, device=dev).half(), torch.randn(N, K, device=dev).half()
+    res = torch.randn(M, N, device=dev).half()
+    if case == "geglu320":
+        w_il, b_il = ops.geglu_interleave(w, torch.zeros(N, device=dev))
+        fn = lambda: ops.linear_geglu(x, w_il, b_il)
+    else:
+        fn = lambda: ops.linear(x, w, None, res)
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(case, "ms", ms, "TF/s", 2.0 * M * N * K / ms / 1e9)
 elif case == "attn_bwd":
     B, heads, d, n = 8, 8, 40, 4096
     dp, d16 = ops.round_dp(d), ops.round_d16(d)
