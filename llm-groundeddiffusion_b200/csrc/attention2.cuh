@@ -8,21 +8,25 @@
 //     m_ref is only raised when the tile maximum exceeds it by more than 8 (log2 units), in which case the O accumulator
 //     in TMEM and the running sum are rescaled by 2^(m_old - m_new) (tcgen05.ld / .st of the row); otherwise P stays
 //     relative to the stale reference (<= 2^8, safe in fp16) and the final 1/l normalises exactly.
-// K/V tiles are shared by both query tiles (half the L2->smem traffic per row).  Same slab layout and outputs as
-// attn_fwd_kernel (attention.cuh).
+// K/V tiles are shared by both query tiles (half the L2->smem traffic per row).  The score row of a tile is read from
+// TMEM once into registers (TMEM reads run at 64 B/clk/SM and are what bounds this kernel at head_dim 40: 64 KB per
+// 128x128 tile), after which S(j+1) is issued into the same TMEM columns while the exponentials of S(j) run.  Same
+// slab layout and outputs as attn_fwd_kernel (attention.cuh).
 #pragma once
 #include "attention.cuh"
 
 namespace b200 {
 
+// P lives in tensor memory (written by tcgen05.st, consumed as the A operand of P.V): the P tile never touches the
+// shared-memory port (32 KB written + 32 KB read per 128x128 tile otherwise), which the S = Q.K^T operand reads and the
+// TMA writes need, and the 64 KB it would occupy go to deeper K/V staging.
 template <int D16, int STAGES>
 struct Attn2Cfg {
   static constexpr int Q_BYTES = 2 * 16384;             // two query tiles, dp = 64
   static constexpr int K_BYTES = 16384;
   static constexpr int V_ATOM = D16 * 128;
   static constexpr int V_BYTES = 2 * V_ATOM;
-  static constexpr int P_BYTES = 2 * 32768;             // one P tile per query tile
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 1024 + 256;
   static constexpr int O_STRIDE = (D16 + 63) / 64 * 64;
 };
 
@@ -36,8 +40,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + STAGES * Cfg::K_BYTES;
-  uint8_t* sP = sV + STAGES * Cfg::V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * Cfg::V_BYTES);
   uint64_t* q_full = bars;                 // 1
   uint64_t* kv_full = bars + 1;            // STAGES
   uint64_t* kv_empty = kv_full + STAGES;   // STAGES
@@ -82,6 +85,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tS[2] = {tmem_base, tmem_base + 128};
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + Cfg::O_STRIDE};
+  const uint32_t tP[2] = {tmem_base + 384, tmem_base + 448};   // 128 keys = 64 packed fp16x2 columns per query tile
 
   if (warp == 0) {
     if (elect_one()) {
@@ -116,14 +120,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto issue_PV = [&](int t, int j) {
       const int stage = j % STAGES;
       if (elect_one()) {
-        const uint32_t paddr = smem_u32(sP) + t * 32768;
         const uint32_t vaddr = smem_u32(sV) + stage * Cfg::V_BYTES;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          const uint64_t ad = make_desc_k_sw128(paddr + a * 16384);
           const uint64_t bd = make_desc_k_sw128(vaddr + a * Cfg::V_ATOM);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tO[t], ad + k * 2, bd + k * 2, idesc_o, (j | a | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)      // 16 keys per MMA: 8 packed columns of P, 32 bytes of the V^T atom
+            umma_f16_ts(tO[t], tP[t] + (a * 4 + k) * 8, bd + k * 2, idesc_o, (j | a | k) ? 1u : 0u);
         }
         tc_commit(&pv_done[t]);
       }
@@ -158,7 +161,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int r = quad * 32 + lane_id();
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     if (t < ntile) {
-      uint8_t* sPt = sP + t * 32768;
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(&s_full[t], j & 1);
@@ -230,15 +232,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             a1 += e1;
             pk[i] = pack_h2(e0, e1);
           }
-          uint8_t* atom = sPt + (c0 >> 6) * 16384;
-          const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0 + q)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          tmem_st_x16(tP[t] + lane_off + (c0 >> 1), pk);   // keys c0..c0+31 -> 16 packed columns
         }
+        tmem_st_wait();
         l += a0 + a1;
-        fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&p_full[t]);
@@ -283,16 +280,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 template <int D16>
 inline void launch_attn_fwd2_t(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVt,
                                const AttnParams& p, int nq, int BH, cudaStream_t st) {
-  using Cfg = Attn2Cfg<D16, 3>;
+  constexpr int ST = 4;
+  using Cfg = Attn2Cfg<D16, ST>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
-  static_assert(256 + 2 * Cfg::O_STRIDE <= 512, "TMEM budget");
+  static_assert(256 + 2 * Cfg::O_STRIDE + 128 <= 512, "TMEM budget");
   static bool done = false;
   if (!done) {
-    cudaFuncSetAttribute(attn_fwd2_kernel<D16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(attn_fwd2_kernel<D16, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     done = true;
   }
   dim3 grid((nq + 255) / 256, BH, 1);
-  attn_fwd2_kernel<D16, 3><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmVt, p);
+  attn_fwd2_kernel<D16, ST><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmVt, p);
 }
 
 }  // namespace b200

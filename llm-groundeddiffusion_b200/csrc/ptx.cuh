@@ -140,6 +140,18 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M=128 rows in the 128 lanes, K 16-bit elements packed two per 32-bit
+// column, 8 columns per K=16 step) comes from tensor memory - used for P.V with P written by tcgen05.st
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor (64-bit):
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4     [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (Blackwell)   [49,52) base offset                  [61,64) layout: 0 none, 2 SW128, 4 SW64, 6 SW32
