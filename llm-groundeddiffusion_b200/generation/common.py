@@ -7,6 +7,10 @@ The B200 UNet, text/VAE/SAM environment are module state set by the driver befor
     import lgd_b200.generation.common as common
     common.configure(unet=B200UNet(...), env=ReferenceEnv(model_dict))   # or SyntheticEnv()
 """
+import os
+import sys
+import time
+
 import numpy as np
 import torch
 
@@ -116,6 +120,15 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
     """Two-phase generation for a batch of specs.  so_guidance / overall_guidance: dict(loss_scale, loss_threshold,
     max_iter, max_index_step, fg_top_p, bg_top_p, fg_weight, bg_weight) or None."""
     net, env = _need()
+    timing = os.environ.get("B200_TIMING")
+    marks = []
+
+    def mark(name):
+        if timing:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     keys = list(keys or P.DEFAULT_GUIDANCE_ATTN_KEYS)
     H, W = height // 8, width // 8
     steps = num_inference_steps
@@ -161,6 +174,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
             so_boxes.append(box)
             so_phrases.append(phrase)
     latents_all_so, masks_so, saved_so, so_imgs = [], [], [], []
+    mark("phase A inputs (host)")
     if owner and (use_ref_ca or frozen_steps > 0):
         gspec = None
         if so_guidance is not None and so_guidance["max_index_step"] > 0:
@@ -170,6 +184,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
                          guidance_scale=guidance_scale, guidance=gspec, gligen=gl, gligen_beta=so_beta,
                          save_keys=[("down", 2, 1, 0)] + (keys if use_ref_ca else []), save_tok=tok_list,
                          save_latents=True, fast_after_steps=fast_after_steps, dynamic_num_inference_steps=True)
+        mark("phase A denoise")
         imgs = env.decode(resA["latents"])
         la = resA["latents_all"].cpu()                         # [steps+1, BA, C, H, W]
         for i in range(len(owner)):
@@ -179,6 +194,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
             latents_all_so.append(la[:, i:i + 1])
             saved_so.append([{k: st[k][i] for k in st} for st in resA["saved"]])     # per step {key: [heads, n]}
 
+    mark("phase A outputs to host, masks")
     # ------------------------------------------------------------------ composition (host bookkeeping)
     composed, frozen_masks, ref_maps, layouts, uncs, conds, glb, glp = [], [], [], [], [], [], [], []
     for b in range(B):
@@ -234,9 +250,14 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
                                ref_word_token_only=True, ref_maps=ref_maps if have_refs else None, **overall_guidance)
     gl = _gligen_inputs(env, glb, glp) if use_gligen else None
     comp_all = torch.cat(composed, dim=1)                      # [steps+1, B, C, H, W]
+    mark("composition (host)")
     resB = P.denoise(net, comp_all[0], torch.cat(uncs, 0), torch.cat(conds, 0), steps, guidance_scale=guidance_scale,
                      guidance=gspec, frozen_mask=torch.stack(frozen_masks, 0), frozen_latents=comp_all,
                      frozen_steps=frozen_steps, gligen=gl, gligen_beta=overall_beta)
+    mark("phase B denoise")
+    if timing:
+        print("[timing] " + ", ".join(f"{n}: {1e3 * (t - marks[i][1]):.0f} ms" for i, (n, t) in enumerate(marks[1:])),
+              file=sys.stderr)
     images = env.decode(resB["latents"])
     outs = []
     for b in range(B):
