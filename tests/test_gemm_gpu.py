@@ -10,7 +10,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (4096, 320, 320), (300, 200, 136),
-                                   (64, 1280, 1280), (2048, 1280, 1280), (77, 640, 768), (1024, 2560, 640)])
+                                   (64, 1280, 1280), (2048, 1280, 1280), (77, 640, 768), (1024, 2560, 640),
+                                   (4096, 960, 320), (4096, 1920, 640)])   # 256-wide tiles, ragged last tile
 def test_linear(cuda, M, N, K):
     from lgd_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
