@@ -153,7 +153,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long long orow = ((long long)b * p.OH + (y * p.sy + p.oy)) * p.OW + (x * p.sx + p.ox);
       asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's staging reads are finished
       if (half == 0) s_orow[r] = row_ok ? orow : -1;
-      const int img = p.rows_per_img > 0 ? (int)(orow / p.rows_per_img) : 0;
+      // rows in the padding of a pixel brick (b >= B, x >= W, y >= H) never store; they take image 0 so that their
+      // per-image channel-add reads stay inside the buffer
+      const int img = (p.rows_per_img > 0 && row_ok) ? (int)(orow / p.rows_per_img) : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");      // s_orow visible
       // coalesced passes: warp ew moves rows ew*16 .. +15, 4 rows per instruction (8 lanes x 16 B per row)
       long long orws[4];
