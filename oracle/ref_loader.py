@@ -53,6 +53,7 @@ def load():
         if p not in sys.path:
             sys.path.insert(0, p)
     torch.Tensor.cuda = lambda self, *a, **k: self  # noqa: identity on CPU
+    torch.nn.Module.cuda = lambda self, *a, **k: self  # utils/boxdiff.py:76 moves its smoothing module to the GPU
 
     proxy = _TorchProxy()
     for name in ("zeros", "ones", "tensor", "empty", "arange", "full", "zeros_like"):

@@ -65,3 +65,20 @@ def test_pipeline_golden():
     res = pipeline_ref.denoise(w, cfg, z0, uncond, cond, 4, g=gc)
     assert res["iters"] == [2, 1, 1, 0]
     assert np.abs(res["latents_all"].numpy() - gold["semantic_latents_all"]).max() < 5e-3
+
+
+def test_boxdiff_goldens():
+    """oracle/boxdiff_ref.py vs the reference's compute_ca_loss_boxdiff outputs frozen in boxdiff_reference.npz"""
+    from oracle import boxdiff_ref
+    from oracle.boxdiff_ref import BOXDIFF_KEYS, boxdiff_inputs
+    gold = np.load(os.path.join(G, "boxdiff_reference.npz"))
+    for seed in (0, 1, 2):
+        maps, bboxes, positions = boxdiff_inputs(seed)
+        leaf = {k: v.clone().requires_grad_(True) for k, v in maps.items()}
+        L = boxdiff_ref.boxdiff_loss(leaf, bboxes, positions, BOXDIFF_KEYS)
+        grads = torch.autograd.grad(L, [leaf[k] for k in BOXDIFF_KEYS])
+        assert abs(float(L) - float(gold[f"s{seed}_loss"])) < 1e-5 * max(1.0, abs(float(L)))
+        for k, gr in zip(BOXDIFF_KEYS, grads):
+            ks = "_".join(map(str, k))
+            np.testing.assert_allclose(gr.sum(dim=1).numpy(), gold[f"s{seed}_g_{ks}"], rtol=1e-3, atol=1e-7)
+            assert abs(float(gr.abs().sum()) - float(gold[f"s{seed}_gabs_{ks}"])) < 1e-3 * float(gold[f"s{seed}_gabs_{ks}"])

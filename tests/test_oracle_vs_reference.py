@@ -192,6 +192,36 @@ def test_gligen_loop_with_ref_attention_matches_reference():
     assert (res["latents"] - lat_ref).abs().max() < 5e-3
 
 
+@pytest.mark.parametrize("seed,smooth", [(0, True), (1, True), (2, False)])
+def test_boxdiff_loss_and_grad_match_reference(seed, smooth):
+    """utils/boxdiff.py compute_ca_loss_boxdiff (no reference-attention term) vs oracle/boxdiff_ref.py: loss and the
+    gradient with respect to every saved map (groundwork for SURVEY section 8 row a14)"""
+    from oracle import boxdiff_ref
+    r = ref_loader.load()
+    g = torch.Generator().manual_seed(100 + seed)
+    heads, n, T = 8, 256, 77
+    keys = [("down", 2, 0, 0), ("down", 2, 1, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+    bboxes = [[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9), (0.0, 0.0, 0.3, 0.3)]]
+    positions = [[2, 3], [6]]
+    maps = {k: torch.softmax(2 * torch.randn(heads, n, T, generator=g), dim=-1) for k in keys}
+
+    ours_in = {k: v.clone().requires_grad_(True) for k, v in maps.items()}
+    ours = boxdiff_ref.boxdiff_loss(ours_in, bboxes, positions, keys, smooth_attentions=smooth)
+    g_ours = torch.autograd.grad(ours, [ours_in[k] for k in keys])
+
+    ref_in = {k: v.clone()[None].requires_grad_(True) for k, v in maps.items()}       # [1, heads, n, T]
+    ref = r.boxdiff.compute_ca_loss_boxdiff(ref_in, bboxes, positions, keys, smooth_attentions=smooth)
+    g_ref = torch.autograd.grad(ref, [ref_in[k] for k in keys])
+    assert abs(float(ours) - float(ref)) < 1e-5 * max(1.0, abs(float(ref))), (float(ours), float(ref))
+    for a, b in zip(g_ours, g_ref):
+        assert (a - b[0]).abs().max() < 1e-6 + 1e-4 * b.abs().max()
+    # update rule (boxdiff.py:228-232)
+    z, gr = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    for index in (0, 7, 24):
+        scale = (1.0 + (0.5 - 1.0) * index / 49) ** 0.5
+        assert torch.allclose(boxdiff_ref.boxdiff_update(z, gr, index, 50), z - 20 * scale / 10 * gr)
+
+
 def test_gligen_loop_fast_schedule_matches_reference():
     """generate_gligen with the thinned timestep list and per-step DDIM step size (fast_after_steps, fast_rate,
     dynamic_num_inference_steps; models/pipelines.py:358-362,439-440)"""
