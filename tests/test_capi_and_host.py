@@ -162,3 +162,44 @@ def test_fast_schedule_host_logic():
     s2.set_timesteps(10)
     s2.apply_fast_schedule(9, 2)                     # cut at or past the end: unchanged
     assert len(s2.timesteps) == 10
+
+
+def test_compose_and_align_match_reference():
+    """utils/latents.py compose_latents (all steps and the fast-schedule prefix) and align_with_bboxes vs latents.py"""
+    import importlib
+    import types
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present")
+    ref_loader.load()
+    RL = importlib.import_module("utils.latents")
+    RL.torch_device = "cpu"
+    from lgd_b200 import latents as L
+    g = torch.Generator().manual_seed(0)
+    steps = 6
+    lat = [torch.randn(steps + 1, 1, 4, 16, 16, generator=g) for _ in range(3)]
+    masks = []
+    for i in range(3):
+        m = torch.zeros(16, 16, dtype=torch.bool)
+        m[2 + i:9 + i, 1 + 2 * i:8 + 2 * i] = True
+        masks.append(m)
+    bg = torch.randn(1, 4, 16, 16, generator=g)
+    md = types.SimpleNamespace(unet=None, scheduler=None, dtype=torch.float32)
+    for fast in (None, 3):
+        ref_c, ref_fg = RL.compose_latents(md, [x.clone() for x in lat], [m.clone() for m in masks], steps, 1, 128, 128,
+                                           latents_bg=bg.clone(), use_fast_schedule=fast is not None,
+                                           fast_after_steps=fast)
+        n = steps if fast is None else fast
+        mine_c, mine_fg = L.compose([x[:n + 1] for x in lat], masks, bg, n)
+        assert torch.equal(ref_c, mine_c) and torch.equal(ref_fg, mine_fg)
+    boxes = [(0.05, 0.1, 0.5, 0.6), (0.4, 0.3, 0.9, 0.8), (0.2, 0.5, 0.7, 0.95)]
+    for horizontal_only in (False, True):
+        rl, rm, ro = RL.align_with_bboxes([x.clone() for x in lat], [m.clone() for m in masks], boxes,
+                                          horizontal_shift_only=horizontal_only)
+        ml, mm, mo = L.align_to_boxes([x.clone() for x in lat], [m.clone() for m in masks], boxes,
+                                      horizontal_only=horizontal_only)
+        for a, b in zip(rl, ml):
+            assert torch.equal(a, b)
+        for a, b in zip(rm, mm):
+            assert torch.equal(a, b)
+        np.testing.assert_allclose(np.array(ro, dtype=np.float64), np.array(mo, dtype=np.float64), rtol=0, atol=1e-7)
