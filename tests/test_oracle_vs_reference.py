@@ -152,6 +152,29 @@ def test_semantic_guidance_loop_matches_reference():
             assert (s_ref[k] - s[k]).abs().max() < 1e-3
 
 
+def test_partial_frozen_loop_matches_reference():
+    """generate_partial_frozen (LMD overall phase, models/pipelines.py:541-599): guidance + CFG + DDIM with the frozen
+    blend z = z_ref[i+1] m + z (1 - m) for index < frozen_steps"""
+    cfg, w, r, md, z0, uncond, cond, _ = _setup_pipeline(False)
+    steps = 4
+    g0 = torch.Generator().manual_seed(21)
+    latents_all = torch.randn(steps + 1, 1, 4, 32, 32, generator=g0)
+    latents_all[0] = z0
+    frozen_mask = (torch.rand(32, 32, generator=g0) > 0.4).float()
+    bboxes = [[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9)]]
+    positions = [[2, 3], [6]]
+    kw = dict(loss_scale=30, loss_threshold=0.2, max_iter=[2, 1], max_index_step=3, guidance_attn_keys=KEYS,
+              fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=4.0, use_ratio_based_loss=False, verbose=False)
+    lat_ref, _ = r.pipelines.generate_partial_frozen(
+        md, latents_all, frozen_mask, (torch.cat([uncond, cond]), uncond, cond), steps, 2, bboxes=bboxes,
+        phrases=["a cat", "a dog"], object_positions=positions, semantic_guidance_kwargs=kw)
+    g = pipeline_ref.GuidanceCfg(bboxes, positions, KEYS, 30, 0.2, [2, 1], 3, 0.2, 0.2, 1.0, 4.0)
+    res = pipeline_ref.denoise(w, cfg, z0, uncond, cond, steps, g=g, frozen_mask=frozen_mask,
+                               frozen_latents=latents_all, frozen_steps=2)
+    assert res["iters"] == [2, 1, 1, 0]
+    assert (res["latents"] - lat_ref).abs().max() < 5e-3
+
+
 def test_gligen_loop_with_ref_attention_matches_reference():
     """generate_gligen (LMD+ overall phase): fuser schedule, null-mask guidance pass, ref-attention loss, frozen blend"""
     cfg, w, r, md, z0, uncond, cond, table = _setup_pipeline(True)
