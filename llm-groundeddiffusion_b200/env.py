@@ -9,7 +9,7 @@ third-party models marked out of scope / "next"), so the path takes them as call
   phrase_indices(prompt, phrases, words, add_suffix) -> (object_positions, word_token_indices, prompt)
                                                                                                    utils/guidance.py:32-89
   decode(latents [B,4,H,W])                     -> uint8 [B, 8H, 8W, 3] or None                    models/pipelines.py:117-127
-  refine_mask(image, box, H, W)                 -> bool [H, W]                                     models/sam.py:174-213
+  refine_mask(image, box, H, W, token_attn)     -> bool [H, W]                                     models/sam.py:113-213
 
 `SyntheticEnv` is the offline stand-in used by tests and bench.py (no CLIP vocabulary, SD weights or SAM weights exist
 in this environment): seeded embeddings, a whitespace tokenizer, the box raster as "SAM" mask, no VAE.
@@ -45,6 +45,10 @@ class SyntheticEnv:
         """same contract as utils/guidance.py:32-89 (suffixing with "| phrase" when absent, last token of the word)"""
         for ph in phrases:
             if ph not in prompt:
+                if not add_suffix:
+                    # the caller has already encoded `prompt` (per-box generation, generation/lmd.py:76-85): a suffix
+                    # added here would shift the token indices away from the encoded text
+                    raise ValueError(f"phrase {ph!r} not found in prompt {prompt!r}")
                 prompt += "| " + ph
         toks = self.tokens(prompt)
         positions, word_idx = [], []
@@ -85,7 +89,7 @@ class SyntheticEnv:
     def decode(self, latents):
         return None
 
-    def refine_mask(self, image, box, H, W):
+    def refine_mask(self, image, box, H, W, token_attn=None):
         return box_to_mask(box, H, W).bool()
 
 
@@ -104,6 +108,10 @@ class ReferenceEnv:
     def phrase_indices(self, prompt, phrases, words=None, add_suffix=True):
         for ph in phrases:
             if ph not in prompt:
+                if not add_suffix:
+                    # the caller has already encoded `prompt` (per-box generation, generation/lmd.py:76-85): a suffix
+                    # added here would shift the token indices away from the encoded text
+                    raise ValueError(f"phrase {ph!r} not found in prompt {prompt!r}")
                 prompt += "| " + ph
         joined = " ".join(self._token_map(prompt))
         positions, word_idx = [], []
@@ -140,7 +148,9 @@ class ReferenceEnv:
         img = (img / 2 + 0.5).clamp(0, 1).float().cpu().permute(0, 2, 3, 1).numpy()
         return (img * 255).round().astype("uint8")
 
-    def refine_mask(self, image, box, H, W):
-        if self._refine is not None and image is not None:
-            return torch.as_tensor(self._refine(image, box)).bool()
+    def refine_mask(self, image, box, H, W, token_attn=None):
+        """refine_mask(image, box, token_attn) -> [H, W] mask: the SAM step between the phases (models/sam.py:113-213;
+        LMD prompts SAM with points from `token_attn`, LMD+ with the box).  Without a callable: the box raster."""
+        if self._refine is not None:
+            return torch.as_tensor(self._refine(image, box, token_attn)).bool()
         return box_to_mask(box, H, W).bool()

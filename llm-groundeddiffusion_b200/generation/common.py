@@ -41,7 +41,22 @@ def _need():
     return _state["unet"], _state["env"]
 
 
-_NUM = ["zero", "one", "two", "three", "four", "five", "six", "seven", "eight", "nine", "ten", "eleven", "twelve"]
+_ONES = ["zero", "one", "two", "three", "four", "five", "six", "seven", "eight", "nine", "ten", "eleven", "twelve",
+         "thirteen", "fourteen", "fifteen", "sixteen", "seventeen", "eighteen", "nineteen"]
+_TENS = ["", "", "twenty", "thirty", "forty", "fifty", "sixty", "seventy", "eighty", "ninety"]
+
+
+def _number_words(n):
+    """inflect.engine().number_to_words for the counts a layout can hold (utils/parse.py:342)"""
+    try:
+        import inflect
+        return inflect.engine().number_to_words(n)
+    except Exception:
+        if n < 20:
+            return _ONES[n]
+        if n < 100:
+            return _TENS[n // 10] + ("-" + _ONES[n % 10] if n % 10 else "")
+        return str(n)
 
 
 def _plural(noun):
@@ -73,7 +88,7 @@ def convert_spec(spec, height=512, width=512):
         bxs = [box for nn, box in conv if nn == n]
         if len(bxs) > 1:
             ph = _plural(n.replace("an ", "").replace("a ", ""))
-            ph = (_NUM[len(bxs)] if len(bxs) < len(_NUM) else str(len(bxs))) + " " + ph
+            ph = _number_words(len(bxs)) + " " + ph
         else:
             ph = n
         overall.append((ph, ph.split(" ")[-1], bxs))
@@ -116,9 +131,13 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
                       so_vertical_placement, so_floor_padding, fg_blending_ratio, align_with_overall_bboxes,
                       horizontal_shift_only, use_ref_ca, ref_ca_loss_weight, so_negative_prompt, overall_negative_prompt,
                       guidance_scale=7.5, height=512, width=512, keys=None, overall_prompt_overrides=None,
-                      return_latents=False, use_fast_schedule=False):
+                      return_latents=False, use_fast_schedule=False, sam_attn_key=("down", 2, 1, 0),
+                      sam_attn_start=None):
     """Two-phase generation for a batch of specs.  so_guidance / overall_guidance: dict(loss_scale, loss_threshold,
-    max_iter, max_index_step, fg_top_p, bg_top_p, fg_weight, bg_weight) or None."""
+    max_iter, max_index_step, fg_top_p, bg_top_p, fg_weight, bg_weight) or None.
+    sam_attn_start: LMD hands SAM the word-token attention of `sam_attn_key` averaged over the steps from this index
+    on and over heads (utils/attn.py:9-38 get_token_attnv2, generation/lmd.py:124-147); None = box-prompted SAM (LMD+,
+    generation/lmd_plus.py:123-129)."""
     net, env = _need()
     timing = os.environ.get("B200_TIMING")
     marks = []
@@ -174,6 +193,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
             so_boxes.append(box)
             so_phrases.append(phrase)
     latents_all_so, masks_so, saved_so, so_imgs = [], [], [], []
+    phaseA = None
     mark("phase A inputs (host)")
     if owner and (use_ref_ca or frozen_steps > 0):
         gspec = None
@@ -187,10 +207,18 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
         mark("phase A denoise")
         imgs = env.decode(resA["latents"])
         la = resA["latents_all"].cpu()                         # [steps+1, BA, C, H, W]
+        tok_attn = None
+        if sam_attn_start is not None:
+            # utils/attn.py:9-38: mean over the saved steps [start:] then over heads, reshaped to the key's grid
+            st = torch.stack([s_[sam_attn_key] for s_ in resA["saved"][sam_attn_start:]], 0).float().mean(0).mean(1)
+            side = int(round(st.shape[1] ** 0.5))
+            tok_attn = st.view(-1, side, side).cpu().numpy()
+        phaseA = dict(latents=resA["latents"], state=resA["state"], token_attn=tok_attn)
         for i in range(len(owner)):
             img = imgs[i] if imgs is not None else None
             so_imgs.append(img)
-            masks_so.append(env.refine_mask(img, so_boxes[i], H, W))
+            masks_so.append(torch.as_tensor(env.refine_mask(
+                img, so_boxes[i], H, W, token_attn=tok_attn[i] if tok_attn is not None else None)).bool())
             latents_all_so.append(la[:, i:i + 1])
             saved_so.append([{k: st[k][i] for k in st} for st in resA["saved"]])     # per step {key: [heads, n]}
 
@@ -266,5 +294,6 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
         if return_latents:
             o["latents"] = resB["latents"][b:b + 1]
             o["guidance_state"] = resB["state"]
+            o["phase_a"] = dict(index=idx, masks=[masks_so[i] for i in idx], **(phaseA or {}))
         outs.append(o)
     return outs

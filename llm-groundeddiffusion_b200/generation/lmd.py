@@ -6,6 +6,8 @@ from .common import DEFAULT_OVERALL_NEGATIVE_PROMPT, DEFAULT_SO_NEGATIVE_PROMPT
 
 version = "lmd"
 _MAX_ITER = [4] * 5 + [3] * 5 + [2] * 5 + [2] * 5 + [1] * 10
+# generation/lmd.py:36-37: the word-token attention handed to SAM is averaged over the steps from this index on
+attn_aggregation_step_start = 10
 
 
 def run_batch(specs, bg_seeds, fg_seed_starts, overall_prompt_overrides=None, frozen_step_ratio=0.5,
@@ -31,7 +33,8 @@ def run_batch(specs, bg_seeds, fg_seed_starts, overall_prompt_overrides=None, fr
         fg_blending_ratio=fg_blending_ratio, align_with_overall_bboxes=align_with_overall_bboxes,
         horizontal_shift_only=horizontal_shift_only, use_ref_ca=use_ref_ca, ref_ca_loss_weight=ref_ca_loss_weight,
         so_negative_prompt=so_negative_prompt, overall_negative_prompt=overall_negative_prompt,
-        overall_prompt_overrides=overall_prompt_overrides, return_latents=return_latents, use_fast_schedule=use_fast_schedule)
+        overall_prompt_overrides=overall_prompt_overrides, return_latents=return_latents,
+        use_fast_schedule=use_fast_schedule, sam_attn_start=attn_aggregation_step_start)
 
 
 def run(spec, bg_seed=1, overall_prompt_override="", fg_seed_start=20, **kwargs):

@@ -777,7 +777,8 @@ class B200UNet:
         rows = B * N
         f = lambda x: x.to(self.dev, torch.float32).contiguous()
         x = torch.empty(rows, D + 64, device=self.dev, dtype=torch.float16)
-        check(lib().b200lmd_position_embed(ptr(f(boxes)), ptr(f(masks)), ptr(f(emb)),
+        bx, mk, em = f(boxes), f(masks), f(emb)      # locals keep the converted copies alive across the launch
+        check(lib().b200lmd_position_embed(ptr(bx), ptr(mk), ptr(em),
                                            ptr(self.w["position_net.null_positive_feature"]),
                                            ptr(self.w["position_net.null_position_feature"]), ptr(x), _i(rows), _i(D),
                                            cur_stream()))

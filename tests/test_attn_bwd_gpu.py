@@ -22,7 +22,11 @@ def _slabs(B, heads, d, n, dev):
 @pytest.mark.parametrize("B,heads,d,nq,nk,nk_store", [(2, 8, 40, 1024, 1024, None), (1, 8, 80, 256, 256, None),
                                                       (2, 8, 160, 256, 256, None), (1, 8, 160, 64, 64, None),
                                                       (1, 8, 16, 256, 286, 256), (2, 5, 64, 320, 320, None),
-                                                      (1, 8, 32, 64, 94, 64)])
+                                                      (1, 8, 32, 64, 94, 64),
+                                                      # the shapes the guidance step runs at SD1.5 widths, batch 8:
+                                                      # 64x64 self-attention and the fuser's 4096+30 ragged tokens
+                                                      (8, 8, 40, 4096, 4096, None), (2, 8, 40, 4126, 4126, None),
+                                                      (2, 8, 80, 1054, 1054, None), (2, 8, 160, 286, 286, None)])
 def test_self_attention_bwd(cuda, B, heads, d, nq, nk, nk_store):
     from lgd_b200 import ops
     C = heads * d

@@ -13,7 +13,9 @@ def _rel(a, b):
 @pytest.mark.parametrize("B,heads,d,nq,nk,cross", [
     (2, 8, 40, 4096, 4096, False), (2, 8, 80, 1024, 1024, False), (2, 8, 160, 256, 256, False),
     (3, 8, 160, 64, 64, False), (2, 8, 40, 4096, 77, True), (2, 8, 160, 256, 77, True), (1, 8, 16, 256, 286, False),
-    (2, 5, 64, 1024, 1024, False), (1, 8, 32, 64, 94, False), (2, 8, 64, 576, 576, False)])
+    (2, 5, 64, 1024, 1024, False), (1, 8, 32, 64, 94, False), (2, 8, 64, 576, 576, False),
+    (2, 8, 40, 4126, 4126, False), (2, 8, 80, 1054, 1054, False), (2, 8, 160, 286, 286, False),   # fuser: n + 30
+    (1, 5, 64, 9216, 9216, False)])                                                                  # SD2.1 at 96x96
 def test_attention_fwd(cuda, B, heads, d, nq, nk, cross):
     from lgd_b200 import ops
     C = heads * d

@@ -1,0 +1,243 @@
+"""GPU parity at the REAL widths of the BASELINE configs (the network-level tests in test_unet_gpu.py use a 128..512
+wide topology): SD1.5 + GLIGEN (320/640/1280 channels, head_dim 40/80/160, 64x64 latents, K=2560/1920 concat convs,
+the d=160 fused cross-attention+loss kernel and its backward inside the network) and SD2.1 at 96x96 latents, against the
+CPU fp32 oracle (oracle/unet_ref.py, pinned to the reference) run live on the host cores.  Tolerances: fp16 activations
+/ fp32 accumulation vs fp32, stated per check; measured values are recorded in DESIGN.md section 7."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+_report = {}
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _note(k, v):
+    _report[k] = v
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "fullwidth_parity.json"), "w") as f:
+        json.dump(_report, f, indent=1)
+
+
+@pytest.fixture(scope="module")
+def sd15(cuda):
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import unet_ref
+    torch.set_num_threads(min(os.cpu_count() or 1, 64))
+    ocfg = unet_ref.UNetConfig.sd15(gligen=True)
+    w = unet_ref.make_weights(ocfg, seed=0)
+    net = B200UNet(UNetConfig.sd15(gligen=True), w, "cuda:0")
+    return ocfg, w, net
+
+
+def _gligen(B, g):
+    boxes = torch.zeros(B, 30, 4)
+    masks = torch.zeros(B, 30)
+    emb = torch.zeros(B, 30, 768)
+    for b in range(B):
+        n = 2 + b
+        xy = torch.rand(n, 2, generator=g) * 0.5
+        boxes[b, :n] = torch.cat([xy, xy + 0.2 + 0.3 * torch.rand(n, 2, generator=g)], 1)
+        masks[b, :n] = 1
+        emb[b, :n] = torch.randn(n, 768, generator=g)
+    return dict(boxes=boxes, masks=masks, positive_embeddings=emb)
+
+
+def test_sd15_gligen_cfg_forward_matches_oracle(cuda, sd15):
+    """one CFG forward ([uncond; cond], fusers on) at SD1.5+GLIGEN widths, 64x64 latents, B=2: eps and all 16 maps"""
+    from oracle import unet_ref
+    ocfg, w, net = sd15
+    B, side = 2, 64
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(B, 4, side, side, generator=g)
+    text = torch.randn(2 * B, 77, 768, generator=g)
+    gl = _gligen(B, g)
+    rep2 = lambda x: torch.cat([x, x], 0)
+    masks2 = rep2(gl["masks"]).clone()
+    masks2[:B] = 0
+    gl2 = dict(boxes=rep2(gl["boxes"]), masks=masks2, positive_embeddings=rep2(gl["positive_embeddings"]))
+    kv = net.set_text(text)
+    objs = net.position_net(gl2["boxes"], gl2["masks"], gl2["positive_embeddings"])
+    t = torch.full((2 * B,), 481.0, device=cuda)
+    eps, saved = net.forward(z.to(cuda), t, kv, rep=2, objs=objs, fuser_on=True, save_keys=None, save_probs=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_saved = {}
+        ref = unet_ref.unet_forward(w, ocfg, torch.cat([z, z], 0), 481, text, gligen=gl2, fuser_on=True,
+                                    saved=ref_saved)
+    r = _rel(eps.permute(0, 3, 1, 2).cpu(), ref)
+    worst = max(float((saved[k]["probs"].float().cpu() - ref_saved[k]).abs().max()) for k in ref_saved)
+    mean = max(float((saved[k]["probs"].float().cpu() - ref_saved[k]).abs().mean()) for k in ref_saved)
+    print("sd15+gligen eps rel-L2", r, "maps max abs", worst, "mean abs", mean)
+    _note("sd15_gligen_cfg_forward", dict(eps_rel_l2=r, maps_max_abs=worst, maps_mean_abs=mean))
+    assert len(saved) == 16
+    assert r < 2e-2, r
+    assert worst < 6e-2, worst
+
+
+@pytest.mark.parametrize("fuser_on", [True, False])
+def test_sd15_guidance_gradient_matches_oracle_autograd(cuda, sd15, fuser_on):
+    """d(loss*scale)/dz through the truncated forward + hand-written backward at SD1.5 widths (fused d=160 kernel on,
+    reference-attention term on, GLIGEN fusers on/off) vs torch autograd through the fp32 oracle, per image"""
+    from lgd_b200 import guidance as G, ops
+    from oracle import guidance_ref, unet_ref
+    ocfg, w, net = sd15
+    B, side, heads = 2, 64, 8
+    assert ops.xattn_fused_supported(heads, 160, 256) and net.use_fused_xattn
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(B, 4, side, side, generator=g)
+    cond = torch.randn(B, 77, 768, generator=g)
+    uncond = torch.randn(B, 77, 768, generator=g)
+    gl = _gligen(B, g)
+    gl_guid = dict(boxes=gl["boxes"], masks=torch.zeros_like(gl["masks"]), positive_embeddings=gl["positive_embeddings"])
+    kv = net.set_text(torch.cat([uncond, cond], 0))
+    objs = net.position_net(gl_guid["boxes"], gl_guid["masks"], gl_guid["positive_embeddings"])
+    layouts = []
+    for b in range(B):
+        bboxes = [[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9), (0.0, 0.0, 0.3, 0.3)]]
+        pos, words = [[2, 3], [6 + b]], [3, 6 + b]
+        refs = [[{k: torch.softmax(3 * torch.randn(heads, 64 if k[0] == "mid" else 256, generator=g), dim=1).numpy()
+                  for k in KEYS} for _ in boxes] for boxes in bboxes]
+        layouts.append(G.SampleLayout(bboxes, pos, words, refs))
+    params = G.LossParams(loss_scale=5.0, fg_weight=1.0, bg_weight=4.0, ref_ca_loss_weight=2.0,
+                          ref_word_token_only=True, use_ref=True)
+    slot_tok, slot_of = G.assign_slots(layouts, params)
+    slot_dev = torch.from_numpy(slot_tok).to(cuda)
+    losses = {k: G.KeyLoss(layouts, slot_dev, slot_of, k, 64 if k[0] == "mid" else 256, heads, len(KEYS), params, cuda,
+                           gscale=net.gscale) for k in KEYS}
+    t = torch.full((B,), 621.0, device=cuda)
+    kv_cond = lambda p: tuple(s[B * heads:] for s in kv.slabs[p])
+    grad, loss = net.guidance_gradient(z.to(cuda), t, kv_cond, losses, objs=objs, fuser_on=fuser_on)
+    torch.cuda.synchronize()
+    grad = (grad.view(B, side, side, 8)[..., :4].permute(0, 3, 1, 2) / net.gscale).cpu()
+    out = {}
+    for b in range(B):
+        zz = z[b:b + 1].clone().requires_grad_(True)
+        saved = {}
+        glb = {k: v[b:b + 1] for k, v in gl_guid.items()}
+        unet_ref.unet_forward(w, ocfg, zz, 621, cond[b:b + 1], gligen=glb, fuser_on=fuser_on, saved=saved,
+                              save_keys=KEYS)
+        refs = [[{k: torch.from_numpy(m[k]) for k in KEYS} for m in obj] for obj in layouts[b].ref_maps]
+        L = guidance_ref.ca_loss({k: v[0] for k, v in saved.items()}, layouts[b].bboxes, layouts[b].object_positions,
+                                 KEYS, 0.2, 0.2, 1.0, 4.0, refs, layouts[b].word_token_indices, 2.0, True) * 5.0
+        gref = torch.autograd.grad(L, [zz])[0]
+        r = _rel(grad[b:b + 1], gref)
+        out[f"image{b}"] = dict(loss=float(loss[b]), loss_oracle=float(L), grad_rel_l2=r)
+        print("sd15 guidance image", b, "loss", float(loss[b]), float(L), "grad rel-L2", r)
+        assert abs(float(loss[b]) - float(L)) < 2e-2 * abs(float(L)), (float(loss[b]), float(L))
+        assert r < 8e-2, r
+    _note(f"sd15_guidance_gradient_fuser_{int(fuser_on)}", out)
+
+
+def test_sd21_forward_96_matches_oracle(cuda):
+    """SD2.1 shapes (heads 5/10/20/20 at head_dim 64, 1024-wide context, Linear proj_in/out) at 96x96 latents
+    (BASELINE config 3 geometry: 9216/2304/576/144 tokens), one CFG forward of one image"""
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import unet_ref
+    torch.set_num_threads(min(os.cpu_count() or 1, 64))
+    ocfg = unet_ref.UNetConfig.sd21()
+    w = unet_ref.make_weights(ocfg, seed=2)
+    net = B200UNet(UNetConfig.sd21(), w, "cuda:0")
+    B, side = 1, 96
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(B, 4, side, side, generator=g)
+    text = torch.randn(2 * B, 77, 1024, generator=g)
+    kv = net.set_text(text)
+    t = torch.full((2 * B,), 301.0, device=cuda)
+    eps, saved = net.forward(z.to(cuda), t, kv, rep=2, save_keys=[("mid", 0, 0, 0), ("up", 1, 2, 0), ("up", 3, 2, 0)],
+                             save_probs=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_saved = {}
+        ref = unet_ref.unet_forward(w, ocfg, torch.cat([z, z], 0), 301, text, saved=ref_saved,
+                                    save_keys=[("mid", 0, 0, 0), ("up", 1, 2, 0), ("up", 3, 2, 0)])
+    r = _rel(eps.permute(0, 3, 1, 2).cpu(), ref)
+    worst = max(float((saved[k]["probs"].float().cpu() - ref_saved[k]).abs().max()) for k in ref_saved)
+    print("sd21 96x96 eps rel-L2", r, "maps max abs", worst)
+    _note("sd21_forward_96", dict(eps_rel_l2=r, maps_max_abs=worst))
+    assert r < 2e-2, r
+    assert worst < 6e-2, worst
+
+
+# ---------------------------------------------------------------------------------------------- kernel shapes the
+# guidance step runs at full width that were only covered inside the small network
+def _tape_grad(net, fn, x, dy):
+    """run fn(x) under the hand-written tape, seed d(out) = dy, return d(x)"""
+    net.tape, net.grads, net._keep = [], {}, []
+    y = fn(x)
+    net.grads[y.data_ptr()] = dy
+    tape, net.tape = net.tape, None
+    for f in reversed(tape):
+        f()
+    gx = net.grads[x.data_ptr()]
+    net.grads, net._keep = {}, []
+    return y, gx
+
+
+def _mini_net(cuda, weights):
+    from lgd_b200.unet import B200UNet, UNetConfig
+    return B200UNet(UNetConfig(), weights, cuda)
+
+
+@pytest.mark.parametrize("B,H,C", [(8, 64, 320), (2, 32, 640), (2, 16, 1280)])
+def test_downsample_conv_dgrad(cuda, B, H, C):
+    """Downsample2D (conv3x3 stride 2 pad 1) forward and its 4-parity transposed dgrad (unet.py conv_down)"""
+    g = torch.Generator().manual_seed(C)
+    w = torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5
+    b = 0.1 * torch.randn(C, generator=g)
+    net = _mini_net(cuda, {"d.conv.weight": w, "d.conv.bias": b})
+    x = torch.randn(B, H, H, C, generator=g).half().to(cuda)
+    dy = torch.randn(B, H // 2, H // 2, C, generator=g).half().to(cuda)
+    y, gx = _tape_grad(net, lambda t: net.conv_down(t, "d.conv"), x, dy)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.half().float().to(cuda)
+    yr = torch.nn.functional.conv2d(xr, wr, b.to(cuda), stride=2, padding=1)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(y, yr.permute(0, 2, 3, 1)) < 2e-3
+    assert _rel(gx, xr.grad.permute(0, 2, 3, 1)) < 3e-3, _rel(gx, xr.grad.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k", [(8, 8, 2560, 1280, 3), (8, 16, 2560, 1280, 3), (8, 16, 1920, 1280, 3),
+                                            (8, 16, 2560, 1280, 1)])
+def test_wide_concat_conv_dgrad(cuda, B, H, Cin, Cout, k):
+    """the K=2560/1920 concat convolutions of up_blocks 0/1 (conv1 3x3 and the 1x1 shortcut): forward + dgrad"""
+    from lgd_b200.unet import TAPS_1x1, TAPS_3x3
+    g = torch.Generator().manual_seed(Cin + k)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (k * k * Cin) ** 0.5
+    b = 0.1 * torch.randn(Cout, generator=g)
+    net = _mini_net(cuda, {"c.weight": w, "c.bias": b})
+    x = torch.randn(B, H, H, Cin, generator=g).half().to(cuda)
+    dy = torch.randn(B, H, H, Cout, generator=g).half().to(cuda)
+    y, gx = _tape_grad(net, lambda t: net.conv(t, "c", taps=TAPS_3x3 if k == 3 else TAPS_1x1), x, dy)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, w.half().float().to(cuda), b.to(cuda), padding=k // 2)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(y, yr.permute(0, 2, 3, 1)) < 2e-3
+    assert _rel(gx, xr.grad.permute(0, 2, 3, 1)) < 3e-3, _rel(gx, xr.grad.permute(0, 2, 3, 1))
+
+
+def test_upsample_conv_dgrad(cuda):
+    """Upsample2D (nearest x2 + conv3x3) forward + backward at the up_blocks.0 shape"""
+    B, H, C = 8, 8, 1280
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5
+    b = 0.1 * torch.randn(C, generator=g)
+    net = _mini_net(cuda, {"u.conv.weight": w, "u.conv.bias": b})
+    x = torch.randn(B, H, H, C, generator=g).half().to(cuda)
+    dy = torch.randn(B, 2 * H, 2 * H, C, generator=g).half().to(cuda)
+    y, gx = _tape_grad(net, lambda t: net.upsample_conv(t, "u.conv"), x, dy)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    up = torch.nn.functional.interpolate(xr, scale_factor=2.0, mode="nearest")
+    yr = torch.nn.functional.conv2d(up, w.half().float().to(cuda), b.to(cuda), padding=1)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(y, yr.permute(0, 2, 3, 1)) < 2e-3
+    assert _rel(gx, xr.grad.permute(0, 2, 3, 1)) < 3e-3, _rel(gx, xr.grad.permute(0, 2, 3, 1))
