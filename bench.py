@@ -6,7 +6,10 @@ One "step" = one full batch of 8 images (Phase A: 32 per-box generations x 50 CF
 40 %; composition; Phase B: 8 overall generations x 50 CFG steps + attention-guidance forward/backward iterations for
 index < 30 + reference-attention transfer).  Synthetic data: seeded random weights with the real layer shapes, seeded
 text embeddings, seeded layouts (no checkpoints, vocabularies or datasets exist offline).  VAE / CLIP / SAM are outside
-the measured path (out of scope / "next"); the SAM mask is the box raster.
+the measured path (out of scope / "next"); the SAM mask is the box raster.  The headline `value` is
+the fixed-iteration mode (B) of SURVEY.md section 8d - overall_loss_threshold=0, so every image runs all 65 guidance
+iterations and the FLOPs behind the number are known; mode (A), the reference's data-dependent thresholds, is timed
+beside it (`mode_a`) with its per-image iteration counts.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 """
@@ -86,9 +89,22 @@ def peaks():
     return 1590.0, 6650.0, "fallback"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one xattn_fused_kernel launch at this shape, from the ncu --set full
-# capture summarised in profiles/ (None until captured)
-XATTN_DRAM_BYTES_NCU = 20.76e6     # dram__bytes_read+write per launch, profiles/r1_ncu_summary.md (ncu --set full)
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE xattn_fused_kernel launch at the roofline shape, read from the
+    committed export of the `ncu --set full` capture (profiles/xattn_fused_ncu_raw.csv, written by
+    profiles/ncu_extract.py from the .ncu-rep of `profiles/bench_xattn.py`); None when no capture is committed."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "xattn_fused_ncu_raw.csv")
+    if not os.path.exists(path):
+        return None, None
+    tot, n = 0.0, 0
+    with open(path) as f:
+        for row in csv.DictReader(f):
+            if "xattn_fused_kernel" not in row.get("kernel", ""):
+                continue
+            tot += float(row["dram_bytes_read"]) + float(row["dram_bytes_write"])
+            n += 1
+    return (tot / n, os.path.relpath(path, ROOT)) if n else (None, None)
 
 
 def xattn_roofline(dev, with_loss=True):
@@ -151,35 +167,117 @@ def xattn_roofline(dev, with_loss=True):
     peak, _, how = peaks()
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
-            "traffic": XATTN_DRAM_BYTES_NCU, "kernel": "xattn_fused_kernel (projections + attention + guidance loss)",
+            "traffic": ncu_dram_traffic()[0], "traffic_source": ncu_dram_traffic()[1], "kernel": "xattn_fused_kernel (projections + attention + guidance loss)",
             "launches_per_op": 1, "ms_per_op": round(ms, 4), "peak_source": how + " (burst, kernel timed alone)",
             "shape": {"B": B, "n": n, "C": C, "heads": heads, "T": T}}
 
 
-def cpu_baseline(sample_forwards=1):
-    """the reference's CPU path (oracle restatement of its UNet/loss in fp32 PyTorch, pinned to the unmodified reference
-    in the build container) on this box's host cores: one conditional UNet forward at SD1.5+GLIGEN shapes, batch 1,
-    extrapolated to one LMD+ image = N*50*2 + 50*2 forward-equivalents + 65 guidance iterations (~2.5 forward-equivalents
-    each: truncated forward + backward)."""
-    from oracle import unet_ref
-    cores = min(os.cpu_count() or 1, 64)       # beyond ~64 threads the fp32 conv/GEMM kernels stop scaling
-    torch.set_num_threads(cores)
-    cfg = unet_ref.UNetConfig.sd15(gligen=True)
-    w = unet_ref.make_weights(cfg, seed=0)
-    g = torch.Generator().manual_seed(0)
-    z = torch.randn(1, 4, 64, 64, generator=g)
-    ctx = torch.randn(1, 77, 768, generator=g)
-    gl = dict(boxes=torch.rand(1, 30, 4, generator=g), masks=torch.zeros(1, 30), positive_embeddings=torch.randn(1, 30, 768, generator=g))
-    with torch.no_grad():
-        unet_ref.unet_forward(w, cfg, z, 500, ctx, gligen=gl)          # warm-up
+# forward passes of ONE LMD+ image at the bench configuration (4 boxes, 50 steps, GLIGEN fusers on for the first 40 % of
+# the steps, models/pipelines.py:408) in fixed-iteration mode: Phase A 4 x 50 CFG passes, Phase B 50 CFG passes and
+# sum(max_iter[:30]) = 65 guidance iterations (55 of them in the steps with the fusers on)
+N_CFG_ON, N_CFG_OFF, N_GUID_ON, N_GUID_OFF = 5 * 20, 5 * 30, 55, 10
+FUSER_OFF_RATIO = 803.0 / 1137.0      # FLOPs of a forward without / with the GLIGEN fusers
+
+
+class CpuArm:
+    """the reference's CPU path (oracle restatement of its UNet / loss / autograd guidance step in fp32 PyTorch, pinned
+    to the unmodified reference in the build container) on this box's host cores, at SD1.5+GLIGEN shapes"""
+
+    def __init__(self):
+        from oracle import unet_ref
+        self.cores = min(os.cpu_count() or 1, 64)       # beyond ~64 threads the fp32 conv/GEMM kernels stop scaling
+        torch.set_num_threads(self.cores)
+        self.cfg = unet_ref.UNetConfig.sd15(gligen=True)
+        self.w = unet_ref.make_weights(self.cfg, seed=0)
+        g = torch.Generator().manual_seed(0)
+        self.z = torch.randn(1, 4, 64, 64, generator=g)
+        self.ctx = torch.randn(2, 77, 768, generator=g)
+        self.gl = dict(boxes=torch.rand(2, 30, 4, generator=g), masks=torch.zeros(2, 30),
+                       positive_embeddings=torch.randn(2, 30, 768, generator=g))
+        self.gl["masks"][1, :4] = 1
+        self.keys = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+
+    def cond_forward(self):
+        """one conditional batch-1 forward (fusers on)"""
+        from oracle import unet_ref
         t0 = time.time()
-        for _ in range(sample_forwards):
-            unet_ref.unet_forward(w, cfg, z, 500, ctx, gligen=gl)
-        dt = (time.time() - t0) / sample_forwards
-    fwd_equiv = 4 * 50 * 2 + 50 * 2 + 65 * 2.5
-    return {"value": 1.0 / (dt * fwd_equiv), "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_forwards} batch-1 fp32 UNet forward(s) at SD1.5+GLIGEN shapes ({dt:.2f} s each), "
-                      f"extrapolated x{fwd_equiv:.0f} forward-equivalents per LMD+ image"}, dt
+        with torch.no_grad():
+            unet_ref.unet_forward(self.w, self.cfg, self.z, 500, self.ctx[1:], gligen={k: v[1:] for k, v in self.gl.items()})
+        return time.time() - t0
+
+    def cfg_forward(self):
+        """one classifier-free-guidance pass: batch 2 = [uncond; cond] (models/pipelines.py:420)"""
+        from oracle import unet_ref
+        t0 = time.time()
+        with torch.no_grad():
+            unet_ref.unet_forward(self.w, self.cfg, torch.cat([self.z, self.z]), 500, self.ctx, gligen=self.gl)
+        return time.time() - t0
+
+    def guidance_iteration(self):
+        """one guidance iteration the way the reference runs it (models/pipelines.py:30-69): full cond-only forward
+        with the 4 guidance maps saved, compute_ca_lossv3 with 4 phrases, autograd to the latent, latent update"""
+        from oracle import guidance_ref, unet_ref
+        t0 = time.time()
+        zz = self.z.clone().requires_grad_(True)
+        saved = {}
+        unet_ref.unet_forward(self.w, self.cfg, zz, 500, self.ctx[1:], gligen={k: v[:1] for k, v in self.gl.items()},
+                              saved=saved, save_keys=self.keys)
+        bboxes = [[(0.1, 0.1, 0.4, 0.5)], [(0.5, 0.1, 0.9, 0.4)], [(0.1, 0.6, 0.45, 0.95)], [(0.55, 0.5, 0.95, 0.9)]]
+        pos = [[1, 2], [3, 4], [5, 6], [7, 8]]
+        L = guidance_ref.ca_loss({k: v[0] for k, v in saved.items()}, bboxes, pos, self.keys, 0.2, 0.2, 1.0, 4.0) * 5.0
+        grad = torch.autograd.grad(L, [zz])[0]
+        _ = (zz - 0.5 * grad).detach()
+        return time.time() - t0
+
+
+def cpu_image_seconds(t_cfg, t_guid):
+    """extrapolation of the timed samples to one LMD+ image (fusers-off passes scaled by the FLOP ratio)"""
+    return (N_CFG_ON + N_CFG_OFF * FUSER_OFF_RATIO) * t_cfg + (N_GUID_ON + N_GUID_OFF * FUSER_OFF_RATIO) * t_guid
+
+
+def cpu_baseline():
+    """bounded sample on the host cores: ONE CFG pass (batch 2) and ONE real guidance iteration (forward + autograd
+    backward + update), after one warm-up forward; extrapolated to one image by the pass counts of the workload."""
+    arm = CpuArm()
+    arm.cond_forward()                               # warm-up (thread pool, allocator)
+    t_cfg = arm.cfg_forward()
+    t_guid = arm.guidance_iteration()
+    sec = cpu_image_seconds(t_cfg, t_guid)
+    return {"value": 1.0 / sec, "unit": "images/s", "cores": arm.cores, "kind": "port",
+            "extrapolated": True, "t_cfg_pass_s": round(t_cfg, 3), "t_guidance_iteration_s": round(t_guid, 3),
+            "sample": f"1 CFG pass (batch 2, {t_cfg:.2f} s) + 1 guidance iteration (forward + autograd backward, "
+                      f"{t_guid:.2f} s) of the fp32 oracle at SD1.5+GLIGEN shapes; EXTRAPOLATED to one LMD+ image = "
+                      f"{N_CFG_ON}+{N_CFG_OFF} CFG passes and {N_GUID_ON}+{N_GUID_OFF} guidance iterations with / without "
+                      f"fusers (fusers-off passes scaled by the FLOP ratio {FUSER_OFF_RATIO:.3f}) = {sec:.0f} s"}
+
+
+def reference_arm(args, config):
+    """--impl reference: the reference's CPU implementation of the path (oracle port - the reference is Python and
+    its third-party model code cannot be installed here) on the host cores.  Each timed step is a
+    bounded sample of the workload - one conditional UNet forward at SD1.5+GLIGEN shapes - and the per-image figure
+    uses the MEASURED cost ratios of a CFG pass and of a real guidance iteration (timed once) to that sample."""
+    arm = CpuArm()
+    for _ in range(max(1, min(args.warmup, 3))):
+        arm.cond_forward()
+    t_cfg = arm.cfg_forward()
+    t_guid = arm.guidance_iteration()
+    t1 = arm.cond_forward()
+    r_cfg, r_guid = t_cfg / t1, t_guid / t1
+    budget_s = 240.0
+    k = max(1, min(args.steps, int(budget_s / max(t1, 1e-3))))
+    ts = [arm.cond_forward() for _ in range(k)]
+    t_fwd = sum(ts) / k
+    sec = cpu_image_seconds(r_cfg * t_fwd, r_guid * t_fwd)
+    base = {"value": 1.0 / sec, "unit": "images/s", "cores": arm.cores, "kind": "port", "extrapolated": True,
+            "sample": f"{k} timed batch-1 conditional forwards ({t_fwd:.2f} s each); a CFG pass costs {r_cfg:.2f} and a "
+                      f"guidance iteration (forward + autograd backward) {r_guid:.2f} of those (both timed once); "
+                      f"EXTRAPOLATED to one LMD+ image = {sec:.0f} s"}
+    line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": base["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": t_fwd * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference", "config": config, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 def main():
@@ -193,25 +291,22 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mode-a", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": WORKLOAD, "batch_per_gpu": args.batch, "boxes_per_prompt": args.boxes,
-              "denoise_steps": args.denoise_steps, "guidance": "reference semantics (data-dependent iteration counts)",
+              "denoise_steps": args.denoise_steps,
+              "guidance": "mode B (SURVEY 8d): overall_loss_threshold=0 -> fixed sum(max_iter[:30]) = 65 guidance "
+                          "iterations per image; mode A (reference thresholds, data-dependent counts) in `mode_a`",
               "l2": "inputs exceed L2 (per-step activations >> 126 MB)", "parallelism": f"dp{world}",
-              "outside_path": "CLIP/VAE/SAM (SAM mask = box raster)"}
+              "unit_note": "an 'image' is the final latent [4,64,64] of one prompt: CLIP/VAE/SAM are outside the "
+                           "measured path (SAM mask = box raster)"}
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        base, dt = cpu_baseline(sample_forwards=max(1, args.steps))
-        line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": base["value"], "unit": "images/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "impl": "reference", "config": config, "cpu_baseline": base,
-                "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        if rank == 0:
+            reference_arm(args, config)
         return
 
     import lgd_b200
@@ -224,6 +319,7 @@ def main():
     from lgd_b200 import parallel
     import torch.distributed as dist
     parallel.init("nccl", dev)
+    pin = parallel.pin_host_threads(local, min(world, torch.cuda.device_count()))
     cfg = UNetConfig.sd15(gligen=True)
     # the only collective on the path: start-up NCCL broadcast of the frozen weights from rank 0
     w = parallel.broadcast_weights(Wt.parameter_shapes(cfg), lambda: Wt.synthetic_weights(cfg, seed=0, device=dev), dev)
@@ -235,13 +331,17 @@ def main():
     seeds = [rank * 1000 + i for i in range(args.batch)]
     fgs = [s + 123456789 for s in seeds]
     io = {"h2d": 0, "d2h": 0}
+    last = {}
 
-    def step(env):
+    def step(env, fixed=True):
         common.configure(net, env)
-        outs = lmd_plus.run_batch(specs, seeds, fgs, num_inference_steps=args.denoise_steps, return_latents=True)
+        kw = dict(overall_loss_threshold=0.0) if fixed else {}
+        outs = lmd_plus.run_batch(specs, seeds, fgs, num_inference_steps=args.denoise_steps, return_latents=True, **kw)
         lat = torch.cat([o["latents"] for o in outs], 0)
         host = lat.cpu()                                  # device -> host read of the step's result
         io["d2h"] = host.numel() * host.element_size()
+        st = outs[0]["guidance_state"]
+        last["iters"] = [int(sum(it[b] for it in st.iters)) for b in range(len(outs))]
         return host
 
     def barrier():
@@ -250,7 +350,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(env, k):
+    def timed(env, k, fixed=True):
         barrier()
         clk = Clocks(local)
         clk.start()
@@ -258,7 +358,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(k):
-            step(env)
+            step(env, fixed)
         e1.record()
         barrier()
         clk.stop_flag = True
@@ -272,23 +372,33 @@ def main():
         torch.cuda.synchronize()
         log(f"warm-up step {i} done")
     ms, launches, clocks = timed(env_res, args.steps)
-    log(f"timed (resident inputs): {ms:.1f} ms for {args.steps} step(s)")
+    iters_b = list(last["iters"])
+    log(f"timed (resident inputs, fixed 65 iterations): {ms:.1f} ms for {args.steps} step(s)")
+    env_host.bytes_out = 0
     ms_e2e, _, _ = timed(env_host, args.steps)
     log(f"timed (host inputs, e2e): {ms_e2e:.1f} ms")
-    io["h2d"] = env_host.bytes_out // max(1, args.steps * 1) if hasattr(env_host, "bytes_out") else 0
+    io["h2d"] = env_host.bytes_out // max(1, args.steps)
     imgs = args.batch * world * args.steps
     line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": imgs / (ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": config, "clocks": clocks, "gpu_launches": launches,
+            "guidance_iterations_per_image": iters_b, "host_threads": pin,
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": io["h2d"],
                     "d2h_bytes_per_step": io["d2h"]}}
+    if not args.no_mode_a:
+        step(env_res, fixed=False)                  # graphs / tables of the data-dependent variant
+        ms_a, _, _ = timed(env_res, 1, fixed=False)
+        line["mode_a"] = {"value": args.batch * world / (ms_a * 1e-3), "unit": "images/s", "ms_per_step": ms_a,
+                          "steps": 1, "guidance_iterations_per_image": list(last["iters"]),
+                          "note": "reference thresholds (overall_loss_threshold 5.0): data-dependent iteration counts"}
+        log(f"timed (mode A): {ms_a:.1f} ms")
     if rank == 0:
         if not args.no_roofline:
             line["roofline"] = xattn_roofline(dev)
             log("roofline micro-benchmark done")
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(1)[0]
+            line["cpu_baseline"] = cpu_baseline()
             log("cpu baseline done")
         print(json.dumps(line))
     if world > 1:

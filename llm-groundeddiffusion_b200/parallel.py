@@ -43,3 +43,59 @@ def max_over_ranks(value, device):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _parse_cpu_list(s):
+    out = []
+    for part in s.split(","):
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def gpu_cpu_affinity():
+    """{gpu index: [cpu ids]} from `nvidia-smi topo -m` (the 'CPU Affinity' column); {} when unavailable"""
+    import re
+    import subprocess
+    try:
+        txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return {}
+    aff = {}
+    for line in txt.splitlines():
+        m = re.match(r"^GPU(\d+)\s", line)
+        if not m:
+            continue
+        for tok in re.split(r"\s+", line.strip())[1:]:
+            if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", tok) and ("-" in tok or "," in tok):
+                aff[int(m.group(1))] = _parse_cpu_list(tok)
+                break
+    return aff
+
+
+def pin_host_threads(local_rank, ranks_on_node, max_threads=8):
+    """One process per GPU: keep each rank's host work (latent composition, table building, launch loop) on its own
+    slice of the cores that are local to its GPU, and cap torch's intra-op pool, so that N independent replicas do not
+    contend for the same cores (round-1 scaling loss was host contention: eight ranks x all-core thread pools, ranks
+    not NUMA-local).  Single-rank runs keep the full affinity (the CPU baseline uses all cores).
+    Returns a short description for the bench line."""
+    ncpu = os.cpu_count() or 1
+    if ranks_on_node <= 1:
+        torch.set_num_threads(min(16, ncpu))
+        return {"pinned": False, "torch_threads": torch.get_num_threads()}
+    aff = gpu_cpu_affinity()
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = list(range(ncpu))
+    mine = [c for c in aff.get(local_rank, avail) if c in set(avail)] or avail
+    peers = [r for r in range(ranks_on_node) if aff.get(r, avail) == aff.get(local_rank, avail)] or [local_rank]
+    k = peers.index(local_rank) if local_rank in peers else 0
+    per = max(1, len(mine) // len(peers))
+    cpus = mine[k * per:(k + 1) * per] or mine
+    try:
+        os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, min(max_threads, len(cpus))))
+    return {"pinned": True, "cpus": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})", "torch_threads": torch.get_num_threads()}

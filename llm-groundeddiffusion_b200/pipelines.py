@@ -16,6 +16,9 @@ The only host<->device traffic inside a step is the per-image loss read-back tha
 (loss.item(), pipelines.py:30).
 """
 import ctypes
+import os
+import sys
+import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -93,7 +96,10 @@ class CudaGraph:
 
     _warmed = set()
 
+    capture_seconds = 0.0      # wall time spent warming + capturing (B200_TIMING bookkeeping)
+
     def __init__(self, fn, key=None):
+        t0 = time.perf_counter()
         if key is None or key not in CudaGraph._warmed:
             fn()                               # first use of this launch sequence: eager run (one-time kernel
             torch.cuda.synchronize()           # attributes, driver entry points, allocator warm-up)
@@ -102,6 +108,7 @@ class CudaGraph:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = fn()
+        CudaGraph.capture_seconds += time.perf_counter() - t0
 
     def __call__(self):
         self.graph.replay()
@@ -213,6 +220,10 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
     re-derived per step, latents kept only for index < fast_after_steps.
     Returns dict(latents, latents_all, saved, state)."""
     dev = net.dev
+    timing = os.environ.get("B200_TIMING")
+    if timing:
+        torch.cuda.synchronize()
+        t_start, cap0 = time.perf_counter(), CudaGraph.capture_seconds
     z = z0.to(dev, torch.float32).contiguous().clone()
     B, Cz, H, W = z.shape
     sched = DDIMSchedule(prediction_type)
@@ -247,6 +258,9 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
     t2 = torch.empty(2 * B, device=dev, dtype=torch.float32)
     latents_all = [z.clone()] if save_latents else None
     saved_all = []
+    if timing:
+        torch.cuda.synchronize()
+        t_loop = time.perf_counter()
     for index, t in enumerate(sched.timesteps):
         fuser_on = gligen is not None and index < n_ground
         if guidance is not None:
@@ -275,5 +289,11 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
                                            cur_stream()))
         if save_latents and (fast_after_steps is None or index < fast_after_steps):
             latents_all.append(z.clone())
+    if timing:
+        torch.cuda.synchronize()
+        t_end = time.perf_counter()
+        print(f"[timing] denoise B={B}: setup {1e3 * (t_loop - t_start):.0f} ms, loop {1e3 * (t_end - t_loop):.0f} ms "
+              f"(of which graph warm-up+capture {1e3 * (CudaGraph.capture_seconds - cap0):.0f} ms), guidance "
+              f"iterations {int(np.sum(state.iters)) if state.iters else 0}", file=sys.stderr)
     return dict(latents=z, latents_all=torch.stack(latents_all, 0) if save_latents else None, saved=saved_all,
                 state=state)

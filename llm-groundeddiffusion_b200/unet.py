@@ -476,6 +476,8 @@ class B200UNet:
         ptok = torch.zeros(B * heads, n, device=self.dev, dtype=torch.float16) if tok is not None else None
         lse = torch.zeros(B * heads, na, device=self.dev, dtype=torch.float32) if rec else None
         fused = self.use_fused_xattn and T <= 80 and k.shape[1] >= 80 and ops.xattn_fused_supported(heads, d, n)
+        # loss.c is None for an external-gradient holder (adapter.py): d loss / dP arrives through loss.dp_extra
+        loss_c = ctypes.byref(loss.c) if (loss is not None and getattr(loss, "c", None) is not None) else None
         if fused:
             # whole op in ONE launch (csrc/xattn_fused.cuh): to_q, QK^T, softmax, loss, PV, to_out + bias + residual
             q = torch.zeros(B * heads, na, ops.round_dp(d), device=self.dev, dtype=torch.float16) if rec else None
@@ -484,7 +486,7 @@ class B200UNet:
             check(lib().b200lmd_xattn_fused_f16(
                 ptr(xn), ptr(self.w[prefix + ".to_q.w"]), ptr(k), ptr(vt), ptr(self.w[prefix + ".to_out.0.w"]),
                 ptr(self.w[prefix + ".to_out.0.bias"]), ptr(residual), ptr(y), ptr(o), ptr(q), ptr(lse), ptr(probs),
-                ptr(tok), ptr(ptok), ctypes.byref(loss.c) if loss is not None else None, _i(B), _i(n), _i(heads),
+                ptr(tok), ptr(ptok), loss_c, _i(B), _i(n), _i(heads),
                 _i(d), _i(T), _i(k.shape[1]), _f(scale), cur_stream()))
         else:
             q, _ = self._slabs(B * heads, na, d, True, False, slot="xq")
@@ -492,7 +494,7 @@ class B200UNet:
                  heads=heads, head_dim=d, which0=0, rm=(q, None, None))
             o = torch.empty(M, C, device=self.dev, dtype=torch.float16)
             check(lib().b200lmd_xattn_fwd_f16(ptr(q), ptr(k), ptr(vt), ptr(o), _i(C), ptr(lse), ptr(probs), ptr(tok),
-                                              ptr(ptok), ctypes.byref(loss.c) if loss is not None else None, _i(B),
+                                              ptr(ptok), loss_c, _i(B),
                                               _i(heads), _i(n), _i(T), _i(na), _i(k.shape[1]), _i(d), _f(scale),
                                               cur_stream()))
         if save is not None:
@@ -722,26 +724,36 @@ class B200UNet:
         eps = self._network(z, t, rep, st)
         return eps, saved
 
-    def guidance_gradient_launch(self, z, t, kv_cond, losses: Dict[tuple, "G.KeyLoss"], objs=None, fuser_on=False):
-        """launch-only part (CUDA-graph capturable: no host synchronisation): cond-only pass truncated at the last
-        guidance key + hand-written backward.  Returns (grad fp32 NHWC-8 [B, HW, 8] = gscale * d(loss*loss_scale)/dz,
-        loss partials [n_keys, B*heads] on the device)"""
+    def guidance_forward(self, z, t, kv_cond, losses, objs=None, fuser_on=False, save=None):
+        """cond-only pass truncated at the last guidance key with the hand-written tape recording; returns the tape"""
         self.tape, self.grads, self._keep = [], {}, []
         self.latent_grad = None
         order = [k for _, k in self._key_order() if k in losses]
         self._last_key = order[-1]
-        st = dict(kv=kv_cond, objs=objs, fuser_on=fuser_on, loss=losses, save=None)
+        st = dict(kv=kv_cond, objs=objs, fuser_on=fuser_on, loss=losses, save=save)
         try:
             self._network(z, t, 1, st)
             raise RuntimeError("guidance keys never reached")
         except _Truncate:
             pass
         tape, self.tape = self.tape, None
+        return tape, order
+
+    def guidance_backward(self, tape):
+        """replay the tape backwards (dgrad only - weights are frozen) down to d loss / d latent (fp32 NHWC-8, x gscale)"""
         for fn in reversed(tape):
             fn()
-        parts = torch.stack([losses[k].loss_part for k in order])
         g = self.latent_grad
         self.grads, self._keep = {}, []
+        return g
+
+    def guidance_gradient_launch(self, z, t, kv_cond, losses: Dict[tuple, "G.KeyLoss"], objs=None, fuser_on=False):
+        """launch-only part (CUDA-graph capturable: no host synchronisation): cond-only pass truncated at the last
+        guidance key + hand-written backward.  Returns (grad fp32 NHWC-8 [B, HW, 8] = gscale * d(loss*loss_scale)/dz,
+        loss partials [n_keys, B*heads] on the device)"""
+        tape, order = self.guidance_forward(z, t, kv_cond, losses, objs=objs, fuser_on=fuser_on)
+        g = self.guidance_backward(tape)
+        parts = torch.stack([losses[k].loss_part for k in order])
         return g, parts
 
     @staticmethod

@@ -299,3 +299,43 @@ def test_fast_schedule_matches_reference():
                     ours.adjust(index, t)
                     assert ours.num_inference_steps == s.num_inference_steps
     assert r is not None
+
+
+def test_callshape_loop_matches_reference_pipeline():
+    """oracle/callshape_ref.generate (the loop used to test the B200UNetAdapter on the GPU box) drives the UNMODIFIED
+    reference UNet module through the reference's own call shape and must reproduce the unmodified
+    pipelines.generate_gligen: same iteration counts, same latents, same saved maps"""
+    from oracle import callshape_ref
+    cfg, w, r, md, z0, uncond, cond, table = _setup_pipeline(True)
+    steps = 4
+    bboxes_flat = [(0.1, 0.2, 0.6, 0.7), (0.5, 0.4, 0.95, 0.9)]
+    sg_bboxes = [[bboxes_flat[0]], [bboxes_flat[1]]]
+    positions = [[2, 3], [6]]
+    kw = dict(loss_scale=5, loss_threshold=0.01, max_iter=[2, 1], max_index_step=3, guidance_attn_keys=KEYS,
+              fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=4.0, use_ratio_based_loss=False, verbose=False)
+    lat_ref, _, saved_ref = r.pipelines.generate_gligen(
+        md, z0, (uncond, cond), steps, bboxes_flat, ["a cat", "a dog"], gligen_scheduled_sampling_beta=0.5,
+        semantic_guidance=True, semantic_guidance_bboxes=sg_bboxes, semantic_guidance_object_positions=positions,
+        semantic_guidance_kwargs=kw, show_progress=False, return_saved_cross_attn=True,
+        saved_cross_attn_keys=[("down", 2, 1, 0)] + KEYS, return_cond_ca_only=True, return_token_ca_only=3)
+    boxes = torch.zeros(1, 30, 4)
+    boxes[0, :2] = torch.tensor(bboxes_flat)
+    emb = torch.zeros(1, 30, 768)
+    emb[0, :2] = table[:2]
+    masks = torch.zeros(1, 30)
+    masks[0, :2] = 1
+    g = pipeline_ref.GuidanceCfg(sg_bboxes, positions, KEYS, 5, 0.01, [2, 1], 3, 0.2, 0.2, 1.0, 4.0)
+    res = callshape_ref.generate(md.unet, z0, uncond, cond, steps, g=g,
+                                 gligen=dict(boxes=boxes, masks=masks, positive_embeddings=emb), gligen_beta=0.5,
+                                 saved_cross_attn_keys=[("down", 2, 1, 0)] + KEYS, return_token_ca_only=3,
+                                 fuser_types=(r.attention.GatedSelfAttentionDense,))
+    assert res["iters"] == [2, 1, 1, 0]
+    assert (res["latents"] - lat_ref).abs().max() < 5e-3
+    for s_ref, s in zip(saved_ref, res["saved"]):
+        assert set(s_ref) == set(s)
+        for k in s_ref:
+            assert s_ref[k].shape == s[k].shape and (s_ref[k] - s[k]).abs().max() < 1e-3
+    # and the CPU oracle behind the same call shape (what the GPU-box adapter test compares against)
+    res2 = callshape_ref.generate(callshape_ref.OracleUNet(w, cfg), z0, uncond, cond, steps, g=g,
+                                  gligen=dict(boxes=boxes, masks=masks, positive_embeddings=emb), gligen_beta=0.5)
+    assert res2["iters"] == [2, 1, 1, 0] and (res2["latents"] - lat_ref).abs().max() < 5e-3
