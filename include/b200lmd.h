@@ -193,6 +193,11 @@ int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void* k_slab, c
                             const b200lmd_xattn_loss* loss, int B, int n, int heads, int head_dim, int nk, int k_alloc,
                             float scale, void* stream);
 
+/* The fused kernel's cross-CTA hand-shake counters live in one fixed-size per-device buffer that is allocated on first
+ * use (outside stream capture), zero on entry to every launch and never freed (its address is baked into captured CUDA
+ * graphs).  After a faulted launch call this to re-zero it (host-synchronous). */
+int b200lmd_xattn_fused_reset(void);
+
 /* profiling aid: device buffer [grid][8] of %globaltimer stamps written by the fused kernel (NULL disables) */
 int b200lmd_set_debug_buffer(void* p);
 

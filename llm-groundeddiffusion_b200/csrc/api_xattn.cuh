@@ -83,29 +83,39 @@ inline unsigned long long*& fused_dbg() {
   static unsigned long long* p = nullptr;
   return p;
 }
-// hand-shake counters: zero when allocated, and the kernel leaves them at zero (the last arriver of every counter
-// resets it), so no memset sits between launches; grown on demand outside of capture
-inline int* fused_flags(int n_ints, cudaStream_t st) {
-  static int* buf = nullptr;
-  static int cap = 0;
-  if (n_ints > cap) {
-    if (buf) cudaFree(buf);
-    cap = n_ints < 16384 ? 16384 : n_ints;
-    B200_CHECK(cudaMalloc(&buf, sizeof(int) * cap));
-    B200_CHECK(cudaMemsetAsync(buf, 0, sizeof(int) * cap, st));
+// hand-shake counters + per (image, head, row tile) loss partials of xattn_fused_kernel.  One fixed-size allocation per
+// device, made on first use OUTSIDE stream capture and never freed or regrown: the pointers are baked into captured CUDA
+// graphs, so they must stay valid for the life of the process.  The counters are zero when allocated and the kernel
+// leaves them at zero (the last arriver of every counter resets it), so no memset sits between launches.  The library
+// is single-stream per device: two fused launches never overlap.
+static constexpr int kFusedFlagInts = 1 << 18;       // 2*row_tiles + 16*B ints per launch: up to ~130 k row tiles
+static constexpr int kFusedPartials = 1 << 20;       // row_tiles * 8 floats per launch
+struct FusedScratch {
+  int* flags = nullptr;
+  float* partials = nullptr;
+};
+inline FusedScratch& fused_scratch(cudaStream_t st) {
+  static FusedScratch per_dev[64];
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) throw std::runtime_error("xattn_fused: device index out of range");
+  FusedScratch& s = per_dev[dev];
+  if (!s.flags) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    B200_CHECK(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone)
+      throw std::runtime_error("xattn_fused: first use inside stream capture - run the launch sequence once eagerly "
+                               "before capturing it");
+    B200_CHECK(cudaMalloc(&s.flags, sizeof(int) * kFusedFlagInts));
+    B200_CHECK(cudaMemset(s.flags, 0, sizeof(int) * kFusedFlagInts));
+    B200_CHECK(cudaMalloc(&s.partials, sizeof(float) * kFusedPartials));
   }
-  return buf;
+  return s;
 }
-// per (image, head, row tile) loss partials; never needs zeroing
-inline float* fused_partials(int n) {
-  static float* buf = nullptr;
-  static int cap = 0;
-  if (n > cap) {
-    if (buf) cudaFree(buf);
-    cap = n < 32768 ? 32768 : n;
-    B200_CHECK(cudaMalloc(&buf, sizeof(float) * cap));
-  }
-  return buf;
+/* after a kernel fault (trap) the counters may be left non-zero: re-zero them (host-synchronous) */
+inline void fused_scratch_reset() {
+  FusedScratch& s = fused_scratch((cudaStream_t)0);
+  B200_CHECK(cudaMemset(s.flags, 0, sizeof(int) * kFusedFlagInts));
 }
 inline CUtensorMap rowmajor_map_2d(const __half* p, long long rows, int cols, int ld, int box_rows) {
   uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
@@ -162,11 +172,14 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     p.dbg = fused_dbg();
     // per-row-tile arrival counters live right behind the scratch rows of o_scratch's owner: a small static buffer
     const int n_tiles = (int)(M / 128);
-    p.tile_flags = fused_flags(2 * n_tiles + 2 * B * 8, (cudaStream_t)stream);
+    if (2 * n_tiles + 16 * B > kFusedFlagInts || n_tiles * 8 > kFusedPartials)
+      throw std::runtime_error("xattn_fused: batch exceeds the hand-shake scratch (split the launch)");
+    FusedScratch& fs = fused_scratch((cudaStream_t)stream);
+    p.tile_flags = fs.flags;
     p.tile_done = p.tile_flags + n_tiles;
     p.bh_ready = p.tile_done + n_tiles;
     p.bh_done = p.bh_ready + B * 8;
-    p.loss_partials = fused_partials(n_tiles * 8);
+    p.loss_partials = fs.partials;
     CUtensorMap tmX = rowmajor_map_2d((const __half*)x, M, C, C, 32);
     CUtensorMap tmO = rowmajor_map_2d((const __half*)o_scratch, M, C, C, 32);
     CUtensorMap tmWq = rowmajor_map_2d((const __half*)wq, C, C, C, head_dim);
@@ -184,6 +197,11 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
       default: launch_fused_t<160>(tmX, tmWq, tmK, tmVt, tmO, tmWo, p, row_tiles, st); break;
     }
   });
+}
+
+/* re-zero the fused kernel's hand-shake counters after a faulted launch (host-synchronous) */
+extern "C" int b200lmd_xattn_fused_reset(void) {
+  return b200::guarded([&] { b200::fused_scratch_reset(); });
 }
 
 /* profiling aid: device buffer [grid][8] of %globaltimer stamps written by xattn_fused_kernel (NULL disables) */

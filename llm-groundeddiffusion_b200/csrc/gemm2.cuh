@@ -204,16 +204,19 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld_x32(taddr + 64 + half * 32, gg);
           tmem_ld_wait();
           uint32_t o[16], pv[16], pg[16];
+          float bv[32], bg[32];                  // bias of this thread's 32 value / 32 gate columns (16-byte loads)
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 x4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + half * 32) + q4) : z4;
+            const float4 y4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 64 + half * 32) + q4) : z4;
+            bv[4 * q4] = x4.x; bv[4 * q4 + 1] = x4.y; bv[4 * q4 + 2] = x4.z; bv[4 * q4 + 3] = x4.w;
+            bg[4 * q4] = y4.x; bg[4 * q4 + 1] = y4.y; bg[4 * q4 + 2] = y4.z; bg[4 * q4 + 3] = y4.w;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a0 = __uint_as_float(vv[2 * j]), a1 = __uint_as_float(vv[2 * j + 1]);
-            float g0 = __uint_as_float(gg[2 * j]), g1 = __uint_as_float(gg[2 * j + 1]);
-            if (p.bias) {
-              a0 += __ldg(p.bias + n0 + half * 32 + 2 * j);
-              a1 += __ldg(p.bias + n0 + half * 32 + 2 * j + 1);
-              g0 += __ldg(p.bias + n0 + 64 + half * 32 + 2 * j);
-              g1 += __ldg(p.bias + n0 + 64 + half * 32 + 2 * j + 1);
-            }
+            const float a0 = __uint_as_float(vv[2 * j]) + bv[2 * j], a1 = __uint_as_float(vv[2 * j + 1]) + bv[2 * j + 1];
+            const float g0 = __uint_as_float(gg[2 * j]) + bg[2 * j], g1 = __uint_as_float(gg[2 * j + 1]) + bg[2 * j + 1];
             o[j] = pack_h2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
             pv[j] = pack_h2(a0, a1);
             pg[j] = pack_h2(g0, g1);
@@ -251,17 +254,45 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld_x32(taddr + c0 + half * 32, v);
           tmem_ld_wait();
           const int nh = nb + half * 32;                   // first column of this thread's 32
+          // per-column addend (bias + per-image channel add) of this thread's 32 columns: fetched once per chunk with
+          // 16-byte loads instead of two predicated scalar loads per element (the epilogue of the short-K GEMMs is
+          // bound by its instruction count)
+          const bool has_add = (p.bias != nullptr) || (p.chan_add != nullptr);
+          float add[32];
+          if (has_add) {
+            const float* cadd = p.chan_add ? p.chan_add + (long long)img * p.N : nullptr;
+            if (nh + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nh) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cadd) {
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(cadd + nh) + q4);
+                  b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
+                }
+                add[4 * q4] = b4.x; add[4 * q4 + 1] = b4.y; add[4 * q4 + 2] = b4.z; add[4 * q4 + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int nn = nh + j;
+                float a = 0.f;
+                if (nn < p.N) {
+                  if (p.bias) a += __ldg(p.bias + nn);
+                  if (cadd) a += __ldg(cadd + nn);
+                }
+                add[j] = a;
+              }
+            }
+          }
+          const bool scaled = p.alpha != 1.f;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float a = __uint_as_float(v[g * 8 + j]) * p.alpha;
-              const int nn = nh + g * 8 + j;
-              if (nn < p.N) {
-                if (p.bias) a += __ldg(p.bias + nn);
-                if (p.chan_add) a += __ldg(p.chan_add + (long long)img * p.N + nn);
-              }
+              float a = __uint_as_float(v[g * 8 + j]);
+              if (scaled) a *= p.alpha;
+              if (has_add) a += add[g * 8 + j];
               f[j] = a;
             }
             if (rd) {

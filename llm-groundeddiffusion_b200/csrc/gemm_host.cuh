@@ -122,8 +122,14 @@ inline GemmLaunch build_gemm(const GemmBuild& b, GemmParams ep /* epilogue field
   if (!bn) {
     if (p.mode == EPI_GEGLU) bn = 128;
     else if (b.N <= 64) bn = 64;
-    else if (b.N % 256 == 0 && (long long)m_tiles * (b.N / 256) >= 120) bn = 256;
-    else bn = 128;
+    else {
+      // 256-wide tiles halve the A-operand traffic per FLOP (the short-K projections are bound by bytes in flight from
+      // L2, not by the tensor pipe); taken when the padded last tile wastes at most a tenth of the columns and the
+      // grid still fills the machine
+      const int n256 = (b.N + 255) / 256;
+      const bool small_waste = (n256 * 256 - b.N) * 10 <= b.N;
+      bn = (b.N > 256 && small_waste && (long long)m_tiles * n256 >= 120) ? 256 : 128;
+    }
   }
   L.block_n = bn;
   {

@@ -94,17 +94,20 @@ class CudaGraph:
     """capture a launch-only callable once (after an eager warm-up run) and replay it; all tensors it touches must be
     static (updated in place between replays)"""
 
-    _warmed = set()
-
     capture_seconds = 0.0      # wall time spent warming + capturing (B200_TIMING bookkeeping)
 
-    def __init__(self, fn, key=None):
+    def __init__(self, fn, key=None, owner=None):
+        """key: identifies the launch sequence; owner: the object whose one-time state the sequence initialises (the
+        B200UNet).  The warm-up record lives ON the owner (not in a process-wide set keyed by id(), which a new object
+        can alias after garbage collection): first use of a sequence always runs once eagerly, so kernel attributes,
+        the fused kernel's scratch and the slab cache are set up outside capture."""
         t0 = time.perf_counter()
-        if key is None or key not in CudaGraph._warmed:
+        warmed = owner.__dict__.setdefault("_graph_warm_keys", set()) if owner is not None else None
+        if warmed is None or key is None or key not in warmed:
             fn()                               # first use of this launch sequence: eager run (one-time kernel
             torch.cuda.synchronize()           # attributes, driver entry points, allocator warm-up)
-            if key is not None:
-                CudaGraph._warmed.add(key)
+            if warmed is not None and key is not None:
+                warmed.add(key)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = fn()
@@ -192,7 +195,7 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
             if fuser_on not in state.graphs:
                 state.graphs[fuser_on] = CudaGraph(lambda: net.guidance_gradient_launch(
                     z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on),
-                    key=("guid", id(net), tuple(z.shape), fuser_on, objs is not None))
+                    key=("guid", tuple(z.shape), fuser_on, objs is not None), owner=net)
             grad, parts = state.graphs[fuser_on]()
         else:
             grad, parts = net.guidance_gradient_launch(z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on)
@@ -271,7 +274,7 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
             if fuser_on not in fwd_graphs:
                 fwd_graphs[fuser_on] = CudaGraph(lambda: net.forward(
                     z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys, save_tok=tok_dev),
-                    key=("fwd", id(net), tuple(z.shape), fuser_on, objs_main is not None, save_keys is not None))
+                    key=("fwd", tuple(z.shape), fuser_on, objs_main is not None, save_keys is not None), owner=net)
             eps, saved = fwd_graphs[fuser_on]()
         else:
             eps, saved = net.forward(z, t2, kv, rep=2, objs=objs_main, fuser_on=fuser_on, save_keys=save_keys,

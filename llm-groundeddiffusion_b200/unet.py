@@ -392,16 +392,18 @@ class B200UNet:
         return self.linear(h, prefix + ".net.2", residual=residual, alpha=alpha, bias=out_bias)
 
     # ------------------------------------------------------------------------------------------ attention
-    def _slabs(self, BH, n_alloc, d, rm=True, tr=True, slot=None):
-        """attention operand slabs.  Padding (columns d..dp, rows d..d16) must be zero and is never written, so in
-        forward-only mode (no tape) the zero-filled buffers are cached per (shape, slot) and reused by every layer and
-        step - stream order serialises the layers - instead of memset-ing ~1 GB per attention layer at batch 64."""
+    def _slabs(self, BH, n_alloc, d, rm=True, tr=True, slot=None, owner=None):
+        """attention operand slabs.  Padding (columns d..dp, rows d..d16) must be zero and is never written, so the
+        zero-filled buffers are cached and reused instead of memset-ing them per call (~1 GB per attention layer at
+        batch 64): in forward-only mode one buffer per (shape, slot) serves every layer - stream order serialises the
+        layers; with the tape on, the operands must survive until the layer's backward, so the cache is per layer
+        (`owner`) as well."""
         dp, d16 = ops.round_dp(d), ops.round_d16(d)
 
         def get(kind, shape):
-            if self.tape is not None or slot is None:
+            if slot is None or (self.tape is not None and owner is None):
                 return torch.zeros(shape, device=self.dev, dtype=torch.float16)
-            key = (kind, slot) + tuple(shape)
+            key = (kind, slot, owner if self.tape is not None else None) + tuple(shape)
             t = self._slab_cache.get(key)
             if t is None:
                 t = self._slab_cache[key] = torch.zeros(shape, device=self.dev, dtype=torch.float16)
@@ -416,9 +418,9 @@ class B200UNet:
         d = C // heads
         rec = self.tape is not None
         na = (n + 7) // 8 * 8
-        q, qt = self._slabs(B * heads, na, d, True, rec, slot="q")
-        k, kt = self._slabs(B * heads, na, d, True, rec, slot="k")
-        v, vt = self._slabs(B * heads, na, d, rec, True, slot="v")
+        q, qt = self._slabs(B * heads, na, d, True, rec, slot="q", owner=prefix)
+        k, kt = self._slabs(B * heads, na, d, True, rec, slot="k", owner=prefix)
+        v, vt = self._slabs(B * heads, na, d, rec, True, slot="v", owner=prefix)
         M = B * n
         gemm(xn, (1, 1, M, C, C), self.w[prefix + ".qkv.w"], 3 * C, 1, (1, 1, M), TAPS_1x1, mode=2, rows_per_img=n,
              heads=heads, head_dim=d, which0=0, rm=(q, k, v), tr=(qt, kt, vt))
@@ -437,7 +439,7 @@ class B200UNet:
                     return
                 if residual is not None:
                     self._add_grad(residual, dyv)
-                dO, dOt = self._slabs(B * heads, na, d, True, True)
+                dO, dOt = self._slabs(B * heads, na, d, True, True, slot="dO", owner=prefix)
                 gemm(dyv, (1, 1, M, C, C), self.w[prefix + ".to_out.0.wd"], C, 1, (1, 1, M), TAPS_1x1, mode=2,
                      rows_per_img=n, heads=heads, head_dim=d, which0=0, rm=(dO, None, None), tr=(dOt, None, None),
                      alpha=alpha)
@@ -489,7 +491,7 @@ class B200UNet:
                 ptr(tok), ptr(ptok), loss_c, _i(B), _i(n), _i(heads),
                 _i(d), _i(T), _i(k.shape[1]), _f(scale), cur_stream()))
         else:
-            q, _ = self._slabs(B * heads, na, d, True, False, slot="xq")
+            q, _ = self._slabs(B * heads, na, d, True, False, slot="xq", owner=prefix)
             gemm(xn, (1, 1, M, C, C), self.w[prefix + ".to_q.w"], C, 1, (1, 1, M), TAPS_1x1, mode=2, rows_per_img=n,
                  heads=heads, head_dim=d, which0=0, rm=(q, None, None))
             o = torch.empty(M, C, device=self.dev, dtype=torch.float16)
@@ -519,7 +521,7 @@ class B200UNet:
                 if dyv is not None:
                     if residual is not None:
                         self._add_grad(residual, dyv)
-                    dO, _ = self._slabs(B * heads, na, d, True, False)
+                    dO, _ = self._slabs(B * heads, na, d, True, False, slot="xdO", owner=prefix)
                     gemm(dyv, (1, 1, M, C, C), self.w[prefix + ".to_out.0.wd"], C, 1, (1, 1, M), TAPS_1x1, mode=2,
                          rows_per_img=n, heads=heads, head_dim=d, which0=0, rm=(dO, None, None))
                 self._xattn_bwd(xn, q, k, v, kt, dO, lse, loss, B, heads, n, na, d, scale, prefix, C, M)
