@@ -154,7 +154,7 @@ int b200lmd_attention_fwd_f16(const void* q, const void* k, const void* vt, void
  * Outputs: loss_part[B*heads] (sum over heads and keys = loss * loss_scale), dp_extra[B*heads][n][ext_ld] =
  * gscale * d loss / d P (fed to b200lmd_attention_bwd_f16), optional maps. counters must be zero on first use. */
 typedef struct {
-  int type;            /* 0: fg/bg top-k energy, 1: reference-attention L1 */
+  int type;            /* 0: fg/bg top-k energy, 1: reference-attention L1, 2: ratio-based energy (weight in w_fg) */
   int slot, mask, k_fg, k_bg;
   float w_fg, w_bg, w_ref;
   int ref;

@@ -20,7 +20,7 @@ static constexpr int kMaxSlots = 48;
 static constexpr int kMaxTerms = 80;     // loss terms per image (48 token slots + reference terms)
 
 struct LossTerm {
-  int type;     // 0 = energy (fg/bg top-k), 1 = reference-attention L1
+  int type;     // 0 = energy (fg/bg top-k), 1 = reference-attention L1, 2 = ratio-based energy (w_fg carries the weight)
   int slot;     // which saved column of P
   int mask;     // mask id (row of `masks`)
   int k_fg, k_bg;
@@ -99,7 +99,7 @@ struct LossProb {      // decoded problem
   const float* src;
   const uint8_t* mk;
   const float* R;      // nullptr for energy problems
-  int tok, side, k;
+  int tok, side, k;    // side: 0 fg top-k, 1 bg top-k, 2 ratio-based energy
   float w;
 };
 
@@ -224,6 +224,36 @@ __device__ __forceinline__ float loss_ref(const LossRaw<PERMAX>& q, const LossPr
   return P.w * l1;
 }
 
+// ratio-based energy (utils/guidance.py:122-128, the deprecated default that generation/backward_guidance.py still runs):
+// a = sum_q P M / sum_q P per head, loss = w (1 - a)^2 (w holds scale / (heads T_o n_obj n_keys));
+// d loss / d P_q = -2 w (1 - a) (M_q - a) / sum_q P  - dense over the map
+template <int PERMAX>
+__device__ __forceinline__ float loss_ratio(const LossRaw<PERMAX>& q, const LossProb& P, float* dpx, int ext_ld, int n,
+                                            int per, int lane, float gscale) {
+  const int i0 = lane * per;
+  float* dpx_tok = dpx + P.tok;
+  float sa = 0.f, ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j) {
+    ss += q.v[j];
+    if ((q.m >> j) & 1ull) sa += q.v[j];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const float a = sa / ss;
+  const float g0 = -2.f * P.w * (1.f - a) / ss * gscale;
+#pragma unroll
+  for (int j = 0; j < PERMAX; ++j)
+    if (j < per && i0 + j < n) {
+      const float mq = ((q.m >> j) & 1ull) ? 1.f : 0.f;
+      atomicAdd(dpx_tok + (long long)(i0 + j) * ext_ld, g0 * (mq - a));
+    }
+  return P.w * (1.f - a) * (1.f - a);
+}
+
 constexpr int kLossScratchBytes = 160 * 4 + 160 * 2 + kMaxSlots * 4 + 16 + kMaxTerms * (int)sizeof(LossTerm);
 
 __device__ __forceinline__ LossProb loss_decode(const XattnLoss& L, const LossTerm* sterms, const int* stok,
@@ -239,6 +269,11 @@ __device__ __forceinline__ LossProb loss_decode(const XattnLoss& L, const LossTe
     P.side = sub;
     P.k = sub ? T.k_bg : T.k_fg;
     P.w = sub ? T.w_bg : T.w_fg;
+  } else if (T.type == 2) {
+    P.R = nullptr;
+    P.side = 2;
+    P.k = 1;
+    P.w = T.w_fg;
   } else {
     P.R = L.refs + ((long long)T.ref * heads + h) * n;
     P.side = 0;
@@ -266,7 +301,8 @@ __device__ __forceinline__ void loss_problem_loop(const XattnLoss& L, const Loss
       loss_load(nxt, Pn, n, per, lane);
     }
     const float contrib = P.R ? loss_ref(cur, P, dpx, L.ext_ld, lane, per, L.eps, L.gscale)
-                              : loss_energy(cur, P, dpx, L.ext_ld, n, per, lane, L.gscale);
+                          : (P.side == 2 ? loss_ratio(cur, P, dpx, L.ext_ld, n, per, lane, L.gscale)
+                                         : loss_energy(cur, P, dpx, L.ext_ld, n, per, lane, L.gscale));
     if (lane == 0) prob_loss[pid] = contrib;
     if (more) {
       if (PIPE) {

@@ -79,6 +79,9 @@ class LossParams:
     ref_ca_loss_weight: float = 1.0
     ref_word_token_only: bool = False
     use_ref: bool = False
+    # utils/guidance.py:122-128: the deprecated ratio-based energy (1 - sum(P M)/sum(P))^2, mean over heads; it is what
+    # compute_ca_lossv3 does when the caller does not pass use_ratio_based_loss=False (generation/backward_guidance.py)
+    use_ratio_based_loss: bool = False
 
 
 def assign_slots(samples: Sequence[SampleLayout], params: LossParams):
@@ -117,8 +120,11 @@ def build_key_tables(samples: Sequence[SampleLayout], slot_of, key, n, heads, n_
             T_o = len(s.object_positions[o])
             norm = S / (T_o * n_obj * n_keys)
             for tok in s.object_positions[o]:
-                terms.append((0, slot_of[b][tok], mid, k_fg, k_bg, norm * params.fg_weight, norm * params.bg_weight,
-                              0.0, 0))
+                if params.use_ratio_based_loss:
+                    terms.append((2, slot_of[b][tok], mid, 1, 1, norm / heads, 0.0, 0.0, 0))
+                else:
+                    terms.append((0, slot_of[b][tok], mid, k_fg, k_bg, norm * params.fg_weight,
+                                  norm * params.bg_weight, 0.0, 0))
         if params.use_ref and s.ref_maps is not None and params.ref_ca_loss_weight != 0.0:
             for o in range(n_obj):
                 boxes = _box_list(s.bboxes[o])

@@ -86,6 +86,7 @@ class GuidanceSpec:
     bg_weight: float = 1.0
     ref_ca_loss_weight: float = 1.0
     ref_word_token_only: bool = False
+    use_ratio_based_loss: bool = False     # utils/guidance.py:122-128 (what backward_guidance.py runs)
     # ref_maps[b][phrase][box][step] -> {key: array/tensor [heads, n]} or None
     ref_maps: Optional[list] = None
 
@@ -156,7 +157,7 @@ def build_losses(net, spec: GuidanceSpec, index, H, W, dev):
         refs = spec.ref_maps[b] if use_ref else None       # [phrase][box] -> list over steps of {key: [heads, n]}
         layouts.append(G.SampleLayout(lay.bboxes, lay.object_positions, lay.word_token_indices, refs))
     params = G.LossParams(spec.loss_scale, spec.fg_top_p, spec.bg_top_p, spec.fg_weight, spec.bg_weight,
-                          spec.ref_ca_loss_weight, spec.ref_word_token_only, use_ref)
+                          spec.ref_ca_loss_weight, spec.ref_word_token_only, use_ref, spec.use_ratio_based_loss)
     slot_tok, slot_of = G.assign_slots(layouts, params)
     slot_dev = torch.from_numpy(slot_tok).to(dev)
     out = {k: G.KeyLoss(layouts, slot_dev, slot_of, k, _tokens_of(net, k, H, W), _heads_of(net, k), len(spec.keys),

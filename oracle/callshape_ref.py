@@ -87,7 +87,8 @@ def latent_backward_guidance(sched, unet, cond, index, t, latents, loss, g: pipe
                 one = {k: v[0].float().cpu() for k, v in saved.items()}
                 L = guidance_ref.ca_loss(one, g.bboxes, g.object_positions, g.keys, g.fg_top_p, g.bg_top_p, g.fg_weight,
                                          g.bg_weight, refs, g.word_token_indices, g.ref_ca_loss_weight,
-                                         g.ref_word_token_only) * g.loss_scale
+                                         g.ref_word_token_only,
+                                         use_ratio_based_loss=g.use_ratio_based_loss) * g.loss_scale
                 grad = torch.autograd.grad(L, [latents])[0]
             scale = float((1 - sched.alphas_cumprod[int(t)]) ** 0.5)
             latents = (latents - scale * grad).detach()

@@ -47,7 +47,8 @@ def topk_sizes(mask, fg_top_p, bg_top_p):
 
 
 def ca_loss(saved, bboxes, object_positions, keys, fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0,
-            ref_maps=None, word_token_indices=None, ref_ca_loss_weight=1.0, ref_word_token_only=False, eps=1e-5):
+            ref_maps=None, word_token_indices=None, ref_ca_loss_weight=1.0, ref_word_token_only=False, eps=1e-5,
+            use_ratio_based_loss=False):
     """saved[key]: torch [heads, n, T] (one sample).  ref_maps[obj][box][key]: torch [heads, n] at this timestep.
     Returns the scalar torch loss BEFORE multiplication by loss_scale (pipelines.py:48 multiplies afterwards)."""
     n_obj = len(bboxes)
@@ -65,6 +66,10 @@ def ca_loss(saved, bboxes, object_positions, keys, fg_top_p=0.2, bg_top_p=0.2, f
             obj = torch.zeros((), dtype=torch.float32)
             for tok in object_positions[o]:
                 col = P[:, :, tok]                                             # [heads, n]
+                if use_ratio_based_loss:                                       # utils/guidance.py:122-128
+                    act = (col * m).sum(dim=-1) / col.sum(dim=-1)
+                    obj = obj + torch.mean((1 - act) ** 2)
+                    continue
                 obj = obj + fg_weight * (1 - (col * m).topk(k_fg, dim=1).values.mean(dim=1)).sum()
                 obj = obj + bg_weight * ((col * (1 - m)).topk(k_bg, dim=1).values.mean(dim=1)).sum()
             total = total + obj / len(object_positions[o])

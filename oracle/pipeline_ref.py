@@ -73,6 +73,7 @@ class GuidanceCfg:
     word_token_indices: Optional[list] = None
     ref_ca_loss_weight: float = 1.0
     ref_word_token_only: bool = False
+    use_ratio_based_loss: bool = False     # utils/guidance.py:122-128, the default of compute_ca_lossv3's **kwargs
 
 
 def guidance_iterations(unet: Callable, sched: DDIM, z, t, index, loss, g: GuidanceCfg, trace=None):
@@ -92,7 +93,7 @@ def guidance_iterations(unet: Callable, sched: DDIM, z, t, index, loss, g: Guida
                 refs = [[box[index] for box in obj] for obj in g.ref_maps]
             L = guidance_ref.ca_loss(one, g.bboxes, g.object_positions, g.keys, g.fg_top_p, g.bg_top_p, g.fg_weight,
                                      g.bg_weight, refs, g.word_token_indices, g.ref_ca_loss_weight,
-                                     g.ref_word_token_only) * g.loss_scale
+                                     g.ref_word_token_only, use_ratio_based_loss=g.use_ratio_based_loss) * g.loss_scale
             grad = torch.autograd.grad(L, [z])[0]
             scale = (1 - sched.alphas_cumprod[int(t)]) ** 0.5          # pipelines.py:62-69 (DDIM has no sigmas)
             z = (z - scale * grad).detach()

@@ -339,3 +339,24 @@ def test_callshape_loop_matches_reference_pipeline():
     res2 = callshape_ref.generate(callshape_ref.OracleUNet(w, cfg), z0, uncond, cond, steps, g=g,
                                   gligen=dict(boxes=boxes, masks=masks, positive_embeddings=emb), gligen_beta=0.5)
     assert res2["iters"] == [2, 1, 1, 0] and (res2["latents"] - lat_ref).abs().max() < 5e-3
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ratio_based_loss_matches_reference(seed):
+    """compute_ca_lossv3 with its DEFAULT use_ratio_based_loss=True (what generation/backward_guidance.py runs,
+    utils/guidance.py:122-128): loss and gradient w.r.t. every saved map vs oracle ca_loss(use_ratio_based_loss=True)"""
+    import warnings
+    r = ref_loader.load()
+    saved, bboxes, positions, words, _ = _random_case(seed, with_ref=False)
+    ref_in = {k: v.clone().requires_grad_(True) for k, v in saved.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = r.guidance.compute_ca_lossv3(ref_in, bboxes, positions, KEYS, ref_ca_saved_attns=None,
+                                           word_token_indices=words, ref_ca_loss_weight=0.5, verbose=False)
+    g_ref = torch.autograd.grad(ref, [ref_in[k] for k in KEYS])
+    ours_in = {k: v[0].clone().requires_grad_(True) for k, v in saved.items()}
+    ours = guidance_ref.ca_loss(ours_in, bboxes, positions, KEYS, use_ratio_based_loss=True)
+    g_ours = torch.autograd.grad(ours, [ours_in[k] for k in KEYS])
+    assert abs(float(ours) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    for a, b in zip(g_ours, g_ref):
+        assert (a - b[0]).abs().max() < 1e-7 + 1e-4 * b.abs().max()

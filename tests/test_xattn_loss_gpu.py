@@ -113,3 +113,40 @@ def test_fused_xattn_loss_and_grad(cuda, B, heads, d, n, with_ref):
     tot.backward()
     ref_dq = qg.grad.view(B, heads, n, d).permute(0, 2, 1, 3).reshape(B * n, C) * gscale
     assert _rel(dq.cpu(), ref_dq) < 2e-2, _rel(dq.cpu(), ref_dq)
+
+
+@pytest.mark.parametrize("B,heads,d,n", [(2, 8, 160, 256), (3, 8, 160, 64), (2, 5, 64, 256), (1, 8, 40, 1024)])
+def test_ratio_based_loss_and_grad(cuda, B, heads, d, n):
+    """loss term type 2 - the ratio-based energy of utils/guidance.py:122-128 that backward_guidance.py runs - in the
+    cross-attention kernel: per-image loss and the dense d loss / d P vs autograd through the oracle"""
+    from lgd_b200 import guidance, ops
+    from oracle import guidance_ref
+    C, nk = heads * d, 77
+    g = torch.Generator(device="cpu").manual_seed(n + d + 1)
+    x = torch.randn(B * n, C, generator=g).half().to(cuda)
+    ctx = torch.randn(B * nk, 768, generator=g).half().to(cuda)
+    wq = (torch.randn(C, C, generator=g) * 3 / C ** 0.5).half().to(cuda)
+    wkv = (torch.randn(2 * C, 768, generator=g) * 2 / 768 ** 0.5).half().to(cuda)
+    dp, d16 = ops.round_dp(d), ops.round_d16(d)
+    z = lambda *s: torch.zeros(*s, device=cuda, dtype=torch.float16)
+    q = z(B * heads, n, dp)
+    k, v, kt, vt = z(B * heads, 80, dp), z(B * heads, 80, dp), z(B * heads, d16, 80), z(B * heads, d16, 80)
+    ops.project_heads2(x, wq, n, heads, d, 0, rm=(q, None, None))
+    ops.project_heads2(ctx, wkv, nk, heads, d, 1, rm=(None, k, v), tr=(None, kt, vt))
+    samples = _layouts(B, n + d + 1, heads, n, False)
+    params = guidance.LossParams(loss_scale=30.0, use_ratio_based_loss=True)
+    slot_tok, slot_of = guidance.assign_slots(samples, params)
+    n_keys, gscale = 4, 64.0
+    kl = guidance.KeyLoss(samples, torch.from_numpy(slot_tok).to(cuda), slot_of, KEY, n, heads, n_keys, params, cuda,
+                          gscale=gscale)
+    out, lse, probs, _ = ops.xattn_fwd(q, k, vt, B, heads, n, nk, d, d ** -0.5, loss=kl, want_probs=True, want_lse=True)
+    torch.cuda.synchronize()
+    loss_dev = kl.loss_per_image().cpu()
+    probs_cpu = probs.float().cpu().view(B, heads, n, nk)
+    for b, s in enumerate(samples):
+        Pb = probs_cpu[b].clone().requires_grad_(True)
+        L = guidance_ref.ca_loss({KEY: Pb}, s.bboxes, s.object_positions, [KEY], use_ratio_based_loss=True) * 30.0 / n_keys
+        gP = torch.autograd.grad(L, [Pb])[0]
+        assert abs(float(loss_dev[b]) - float(L)) < 2e-4 * max(1.0, abs(float(L))), (b, float(loss_dev[b]), float(L))
+        dpx = kl.dp_extra.view(B, heads, n, 80)[b, :, :, :nk].cpu() / gscale
+        assert _rel(dpx, gP) < 2e-3, _rel(dpx, gP)
