@@ -193,6 +193,35 @@ int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void* k_slab, c
                             const b200lmd_xattn_loss* loss, int B, int n, int heads, int head_dim, int nk, int k_alloc,
                             float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ BoxDiff loss
+ * utils/boxdiff.py:20-161 (compute_ca_loss_boxdiff -> add_ca_loss_per_attn_map_to_loss_boxdiff ->
+ * _compute_max_attention_per_index + _compute_loss) for B images from the fp16 maps [B*heads, n, T] the guidance forward
+ * saved for each guidance key: key/head average, softmax(100 x) over tokens 1..T-2, optional 3x3 Gaussian (reflect
+ * padding), inner/outer-box top-k means (k = floor(count*P), no clamp), corner (projection) L1; loss[b] (unscaled) and
+ * out_scale * d loss / dP written to every key's dP_extra buffer (the same [n, T] matrix for all keys and heads). */
+typedef struct {
+  int tok;             /* token index of the phrase token in the prompt (1 .. T-2) */
+  int mask;            /* row of masks[n_masks][n]: union-of-boxes cell mask of the phrase */
+  int k_fg, k_bg;
+  int corner;          /* row of corner[n_corner][2*side]: corner_x[side] then corner_y[side] (boxdiff.py:62-65) */
+} b200lmd_boxdiff_term;
+typedef struct {
+  const void* maps[8];        /* fp16 [B*heads, n, T] per key */
+  void* dp_extra[8];          /* fp32 [B*heads, n, ext_ld] per key */
+  int n_keys, heads, n, side, T, ext_ld;
+  const int* img_term_off;    /* [B+1] */
+  const b200lmd_boxdiff_term* terms;
+  const unsigned char* masks;
+  const unsigned char* corner;
+  float* mean;                /* scratch fp32 [B, n, T] */
+  float* dA;                  /* scratch fp32 [B, n, T] */
+  float* loss;                /* [B] */
+  float kern[9];              /* 3x3 smoothing kernel, utils/attn.py:89-115 */
+  int smooth;
+  float out_scale;
+} b200lmd_boxdiff;
+int b200lmd_boxdiff_loss(const b200lmd_boxdiff* p, int B, void* stream);
+
 /* The fused kernel's cross-CTA hand-shake counters live in one fixed-size per-device buffer that is allocated on first
  * use (outside stream capture), zero on entry to every launch and never freed (its address is baked into captured CUDA
  * graphs).  After a faulted launch call this to re-zero it (host-synchronous). */

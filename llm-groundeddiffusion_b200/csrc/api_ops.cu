@@ -3,6 +3,7 @@
 
 #include "../../include/b200lmd.h"
 #include "attention_host.cuh"
+#include "boxdiff.cuh"
 #include "elementwise.cuh"
 #include "gemm_host.cuh"
 
@@ -282,3 +283,25 @@ extern "C" int b200lmd_geglu_bwd_f16(const void* pre, const void* dy, void* dpre
 }
 #include "api_xattn.cuh"
 #include "api_more.cuh"
+
+// ---------------------------------------------------------------------------------------------- BoxDiff loss
+static_assert(sizeof(b200lmd_boxdiff) == sizeof(b200::BoxdiffParams), "C ABI struct mismatch");
+static_assert(sizeof(b200lmd_boxdiff_term) == sizeof(b200::BoxdiffTerm), "C ABI struct mismatch");
+
+extern "C" int b200lmd_boxdiff_loss(const b200lmd_boxdiff* bp, int B, void* stream) {
+  return guarded([&] {
+    const BoxdiffParams& p = *reinterpret_cast<const BoxdiffParams*>(bp);
+    if (p.n_keys < 1 || p.n_keys > kBoxdiffMaxKeys) throw std::runtime_error("boxdiff: 1..8 guidance keys");
+    if (p.side * p.side != p.n || p.n > 1024 || (p.n & 31)) throw std::runtime_error("boxdiff: n must be a square multiple of 32, <= 1024");
+    if (p.T < 3 || p.T > p.ext_ld) throw std::runtime_error("boxdiff: token count out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long per_img = (long long)p.n * p.T;
+    boxdiff_mean_kernel<<<dim3((unsigned)((per_img + 255) / 256), (unsigned)B), 256, 0, st>>>(p);
+    B200_CHECK(cudaGetLastError());
+    const size_t smem = sizeof(float) * (2 * p.n + 2 * p.side + 32) + sizeof(int) * (32 + 2 * p.side);
+    boxdiff_loss_kernel<<<B, p.n, smem, st>>>(p);
+    B200_CHECK(cudaGetLastError());
+    boxdiff_scatter_kernel<<<ew_grid((long long)B * p.heads * per_img), 256, 0, st>>>(p, B);
+    B200_CHECK(cudaGetLastError());
+  });
+}

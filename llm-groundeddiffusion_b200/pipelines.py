@@ -214,7 +214,7 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
 def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional[GuidanceSpec] = None,
             frozen_mask=None, frozen_latents=None, frozen_steps=0, gligen=None, gligen_beta=0.3, save_keys=None,
             save_tok: Optional[Sequence[int]] = None, save_latents=False, prediction_type="epsilon", use_graphs=True,
-            fast_after_steps=None, fast_rate=2, dynamic_num_inference_steps=False):
+            fast_after_steps=None, fast_rate=2, dynamic_num_inference_steps=False, boxdiff=None):
     """B images in lock-step.  z0 [B,4,H,W] fp32 (any device); uncond [1 or B,T,ctx]; cond [B,T,ctx];
     frozen_mask [B,H,W] or [H,W] (1 = take the frozen latent), frozen_latents [steps+1,B,4,H,W];
     gligen: dict(boxes [B,30,4], masks [B,30], positive_embeddings [B,30,768]) of the conditional half;
@@ -222,6 +222,8 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
     return_token_ca_only).  fast_after_steps / fast_rate / dynamic_num_inference_steps: the reference's fast schedule
     (models/pipelines.py:358-362,439-440,449): thinned timestep list after `fast_after_steps`, DDIM step size
     re-derived per step, latents kept only for index < fast_after_steps.
+    boxdiff: a boxdiff.BoxDiffSpec - one BoxDiff guidance step per denoising step for index < max_index_step
+    (utils/boxdiff.py:190-259, models/pipelines.py:186-188) instead of the attention-energy guidance.
     Returns dict(latents, latents_all, saved, state)."""
     dev = net.dev
     timing = os.environ.get("B200_TIMING")
@@ -265,8 +267,31 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
     if timing:
         torch.cuda.synchronize()
         t_loop = time.perf_counter()
+    bd = bd_active = None
+    bd_graphs = {}
     for index, t in enumerate(sched.timesteps):
         fuser_on = gligen is not None and index < n_ground
+        if boxdiff is not None and index < boxdiff.max_index_step and any(len(l.bboxes) for l in boxdiff.layouts):
+            from . import boxdiff as BD
+            if bd is None:
+                bd = BD.BoxDiffLoss(net, boxdiff, H, W, kv.T)
+                bd_active = torch.tensor([int(len(l.bboxes) > 0) for l in boxdiff.layouts], dtype=torch.int32, device=dev)
+                state.t_dev = torch.empty(B, device=dev, dtype=torch.float32)
+                state.boxdiff_losses = []
+            state.t_dev.fill_(float(t))
+            if use_graphs:
+                if fuser_on not in bd_graphs:
+                    bd_graphs[fuser_on] = CudaGraph(lambda: bd.gradient_launch(z, state.t_dev, kv_cond, objs=objs_guid,
+                                                                               fuser_on=fuser_on),
+                                                    key=("boxdiff", tuple(z.shape), fuser_on, objs_guid is not None),
+                                                    owner=net)
+                grad, bl = bd_graphs[fuser_on]()
+            else:
+                grad, bl = bd.gradient_launch(z, state.t_dev, kv_cond, objs=objs_guid, fuser_on=fuser_on)
+            check(lib().b200lmd_latent_update(ptr(z), ptr(grad), _i(grad.shape[2]), _i(B), _i(Cz), _i(H * W),
+                                              _f(BD.step_scale(boxdiff, index, len(sched.timesteps))),
+                                              _f(1.0 / net.gscale), ptr(bd_active), cur_stream()))
+            state.boxdiff_losses.append(bl.clone())
         if guidance is not None:
             latent_backward_guidance(net, sched, z, t, index, kv_cond, guidance, state, objs=objs_guid,
                                      fuser_on=fuser_on, use_graphs=use_graphs)
