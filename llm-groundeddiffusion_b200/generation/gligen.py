@@ -30,7 +30,7 @@ def run_batch(specs, bg_seeds, gligen_scheduled_sampling_beta=0.4, num_inference
         z0.append(L.seeded_noise(seed, net.cfg.in_channels, H, W))
         boxes.append([list(it[3]) for it in so])
         phrases.append([it[1] for it in so])
-    gl = common._gligen_inputs(env, boxes, phrases, ctx=net.cfg.cross_attention_dim)
+    gl = common._gligen_inputs(env, boxes, phrases)
     res = P.denoise(net, torch.cat(z0, 0), torch.cat(uncs, 0), torch.cat(conds, 0), num_inference_steps,
                     guidance_scale=guidance_scale, gligen=gl, gligen_beta=gligen_scheduled_sampling_beta)
     images = env.decode(res["latents"])

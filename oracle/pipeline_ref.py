@@ -107,8 +107,9 @@ def guidance_iterations(unet: Callable, sched: DDIM, z, t, index, loss, g: Guida
 def denoise(w, cfg: unet_ref.UNetConfig, z0, uncond, cond, steps, guidance_scale=7.5, g: Optional[GuidanceCfg] = None,
             frozen_mask=None, frozen_latents=None, frozen_steps=0, gligen=None, gligen_beta=0.3,
             save_keys=None, save_token=None, prediction_type="epsilon", trace=None, fast_after_steps=None,
-            fast_rate=2, dynamic_num_inference_steps=False):
-    """z0 [1,4,H,W]; uncond/cond [1,T,ctx].  Returns dict(latents, latents_all [steps+1], saved (per step), iters).
+            fast_rate=2, dynamic_num_inference_steps=False, boxdiff=None):
+    """z0 [1,4,H,W]; uncond/cond [1,T,ctx].  boxdiff = dict(bboxes, object_positions, keys, max_index_step[, P, L,
+    smooth_attentions]) switches the guidance to utils/boxdiff.py:190-259 (one step per denoising step, sqrt schedule).  Returns dict(latents, latents_all [steps+1], saved (per step), iters).
     gligen: dict(boxes [1,30,4], masks [1,30], positive_embeddings [1,30,768]) for the conditional half.
     Reference quirks reproduced: CFG batch order [uncond; cond] (pipelines.py:420, models.py:85); the guidance pass
     is cond-only and, in GLIGEN mode, sees the ZEROED grounding mask (pipelines.py:317,382-384); fuser is on for
@@ -132,8 +133,22 @@ def denoise(w, cfg: unet_ref.UNetConfig, z0, uncond, cond, steps, guidance_scale
         gl_main = dict(boxes=rep(gligen["boxes"]), positive_embeddings=rep(gligen["positive_embeddings"]), masks=masks2)
         gl_guid = dict(boxes=gl_main["boxes"][:1], positive_embeddings=gl_main["positive_embeddings"][:1],
                        masks=gl_main["masks"][:1])
+    bd_losses = []
     for index, t in enumerate(sched.timesteps):
         fuser_on = gligen is not None and index < n_ground
+        if boxdiff is not None and boxdiff["bboxes"] and index < boxdiff.get("max_index_step", 25):
+            from . import boxdiff_ref
+            zz = z.detach().requires_grad_(True)
+            saved = {}
+            unet_ref.unet_forward(w, cfg, zz, t, cond, gligen=gl_guid, fuser_on=fuser_on, saved=saved,
+                                  save_keys=boxdiff["keys"])
+            L = boxdiff_ref.boxdiff_loss({k: v[0] for k, v in saved.items()}, boxdiff["bboxes"],
+                                         boxdiff["object_positions"], boxdiff["keys"], P=boxdiff.get("P", 0.2),
+                                         L=boxdiff.get("L", 1),
+                                         smooth_attentions=boxdiff.get("smooth_attentions", True)) * 10.0
+            grad = torch.autograd.grad(L, [zz])[0]
+            z = boxdiff_ref.boxdiff_update(z, grad, index, len(sched.timesteps)).detach()
+            bd_losses.append(float(L) / 10.0)
         if g is not None and g.bboxes:
             def guided_unet(zz, tt, keys):
                 saved = {}
@@ -158,4 +173,5 @@ def denoise(w, cfg: unet_ref.UNetConfig, z0, uncond, cond, steps, guidance_scale
                 z = frozen_latents[index + 1] * frozen_mask + z * (1.0 - frozen_mask)
         if fast_after_steps is None or index < fast_after_steps:   # pipelines.py:449
             latents_all.append(z.clone())
-    return dict(latents=z, latents_all=torch.stack(latents_all, 0), saved=saved_all, iters=iters, loss=loss)
+    return dict(latents=z, latents_all=torch.stack(latents_all, 0), saved=saved_all, iters=iters, loss=loss,
+                boxdiff_losses=bd_losses)

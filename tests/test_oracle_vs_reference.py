@@ -360,3 +360,22 @@ def test_ratio_based_loss_matches_reference(seed):
     assert abs(float(ours) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
     for a, b in zip(g_ours, g_ref):
         assert (a - b[0]).abs().max() < 1e-7 + 1e-4 * b.abs().max()
+
+
+def test_boxdiff_loop_matches_reference():
+    """generate_semantic_guidance(use_boxdiff=True) (generation/boxdiff.py:126-137 -> utils/boxdiff.py:190-259): one
+    BoxDiff step per denoising step with the sqrt step schedule, vs oracle pipeline_ref.denoise(boxdiff=...)"""
+    cfg, w, r, md, z0, uncond, cond, _ = _setup_pipeline(False)
+    keys = [("down", 2, 0, 0), ("down", 2, 1, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+    bboxes = [[(0.1, 0.2, 0.6, 0.7)], [(0.5, 0.4, 0.95, 0.9), (0.0, 0.0, 0.4, 0.4)]]
+    positions = [[2, 3], [6]]
+    steps = 4
+    kw = dict(max_index_step=3, ref_ca_word_token_only=True, ref_ca_last_token_only=True, ref_ca_saved_attns=None,
+              word_token_indices=[3, 6], guidance_attn_keys=keys, ref_ca_loss_weight=0.0, verbose=False)
+    lat_ref, _ = r.pipelines.generate_semantic_guidance(
+        md, z0, (torch.cat([uncond, cond]), uncond, cond), steps, bboxes, ["a cat", "a dog"], positions,
+        semantic_guidance_kwargs=kw, use_boxdiff=True, show_progress=False)
+    res = pipeline_ref.denoise(w, cfg, z0, uncond, cond, steps,
+                               boxdiff=dict(bboxes=bboxes, object_positions=positions, keys=keys, max_index_step=3))
+    assert len(res["boxdiff_losses"]) == 3
+    assert (res["latents"] - lat_ref).abs().max() < 5e-3

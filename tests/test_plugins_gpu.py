@@ -1,0 +1,78 @@
+"""GPU parity of the baseline-method plug-ins generation.backward_guidance (ratio-based energy, config 3's method) and
+generation.gligen against the oracle loops (oracle/pipeline_ref.py, pinned to models/pipelines.py of the reference)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+SPECS = [dict(prompt="", gen_boxes=[("a cat", [60, 100, 200, 250]), ("a dog", [280, 200, 200, 220])],
+              bg_prompt="a photo of a park", extra_neg_prompt=""),
+         dict(prompt="", gen_boxes=[("a red ball", [100, 80, 260, 300]), ("a red ball", [20, 300, 150, 150])],
+              bg_prompt="a photo of a beach", extra_neg_prompt="people")]
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _net(gligen, seed=0):
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import unet_ref
+    ocfg = unet_ref.UNetConfig.tiny(gligen=gligen)
+    w = unet_ref.make_weights(ocfg, seed=seed)
+    return ocfg, w, B200UNet(UNetConfig.tiny(gligen=gligen), w, "cuda:0")
+
+
+def test_backward_guidance_plugin(cuda):
+    from lgd_b200.env import SyntheticEnv
+    from lgd_b200.generation import backward_guidance as plug, common
+    from oracle import pipeline_ref
+    import lgd_b200.latents as L
+    ocfg, w, net = _net(False, seed=2)
+    env = SyntheticEnv()
+    common.configure(net, env)
+    steps = 4
+    kw = dict(overall_loss_scale=30, overall_loss_threshold=0.2, overall_max_iter=2, overall_max_index_step=3)
+    outs = plug.run_batch(SPECS, [3, 5], num_inference_steps=steps, return_latents=True, height=256, width=256, **kw)
+    torch.cuda.synchronize()
+    st = outs[0]["guidance_state"]
+    for b, spec in enumerate(SPECS):
+        _, prompt, pwb = common.convert_spec(spec, 256, 256)
+        phrases, words, bboxes = [p for p, _, _ in pwb], [x for _, x, _ in pwb], [x for _, _, x in pwb]
+        pos, widx, prompt = env.phrase_indices(prompt, phrases, words)
+        neg = ((spec["extra_neg_prompt"] + ", ") if spec["extra_neg_prompt"] else "") + common.DEFAULT_OVERALL_NEGATIVE_PROMPT
+        unc, cnd = env.encode_prompts([prompt], neg)
+        g = pipeline_ref.GuidanceCfg([list(map(tuple, x)) for x in bboxes], pos, KEYS, 30, 0.2, 2, 3, use_ratio_based_loss=True)
+        tr = []
+        ref = pipeline_ref.denoise(w, ocfg, L.seeded_noise([3, 5][b], 4, 32, 32), unc, cnd, steps, g=g, trace=tr)
+        ours_iters = [it[b] for it in st.iters]
+        assert ours_iters == ref["iters"], (ours_iters, ref["iters"])
+        first = next(t for t in st.trace if t[3][b])[2][b]
+        assert abs(first - tr[0][2]) < 1e-2 * abs(tr[0][2]), (first, tr[0][2])
+        r = _rel(outs[b]["latents"].cpu(), ref["latents"])
+        print("backward_guidance image", b, "iters", ours_iters, "final-latent rel-L2", r)
+        assert r < 0.1, r
+
+
+def test_gligen_plugin(cuda):
+    from lgd_b200.env import SyntheticEnv
+    from lgd_b200.generation import common, gligen as plug
+    from oracle import pipeline_ref
+    import lgd_b200.latents as L
+    ocfg, w, net = _net(True, seed=0)
+    env = SyntheticEnv()
+    common.configure(net, env)
+    steps = 4
+    outs = plug.run_batch(SPECS, [3, 5], gligen_scheduled_sampling_beta=0.5, num_inference_steps=steps,
+                          return_latents=True, height=256, width=256)
+    torch.cuda.synchronize()
+    for b, spec in enumerate(SPECS):
+        so, prompt, _ = common.convert_spec(spec, 256, 256)
+        neg = ((spec["extra_neg_prompt"] + ", ") if spec["extra_neg_prompt"] else "") + common.DEFAULT_OVERALL_NEGATIVE_PROMPT
+        unc, cnd = env.encode_prompts([prompt], neg)
+        gl = common._gligen_inputs(env, [[list(it[3]) for it in so]], [[it[1] for it in so]])
+        ref = pipeline_ref.denoise(w, ocfg, L.seeded_noise([3, 5][b], 4, 32, 32), unc, cnd, steps, gligen=gl,
+                                   gligen_beta=0.5)
+        r = _rel(outs[b]["latents"].cpu(), ref["latents"])
+        print("gligen image", b, "final-latent rel-L2", r)
+        assert r < 5e-2, r
