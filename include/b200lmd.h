@@ -94,6 +94,13 @@ int b200lmd_cfg_ddim_blend(void* z, const void* eps, int ld_eps, int B, int Cz, 
                            const void* mask, void* stream);
 int b200lmd_latent_update(void* z, const void* grad, int ld_g, int B, int Cz, int HW, float step_scale,
                           float inv_gscale, const int* active, void* stream);
+/* Device-side latent composition between the two phases (utils/latents.py:37-118 compose_latents_with_alignment):
+ * out[s,b,c,y,x] gathers from the per-box trajectory lat[s, owner-1, c, y-dy, x-dx] (zero outside) that owns the cell;
+ * unowned cells are 0 for s > 0 and, for s = 0, the box-mask layer (bowner) over the background latent bg[B,C,H,W].
+ * owner / bowner int32 [B,H,W] (1 + box index, 0 = none; the integer ownership maps are built on the host from the
+ * masks, like the loss tables); shift int32 [BA,2] = (dx, dy) cells.  lat fp32 [S,BA,C,H,W], out fp32 [S,B,C,H,W]. */
+int b200lmd_compose_latents(const void* lat, const void* bg, const int* owner, const int* bowner, const int* shift,
+                            void* out, int S, int BA, int B, int C, int H, int W, void* stream);
 /* GLIGEN PositionNet front end (models/unet_2d_condition.py:63-114): Fourier box features + phrase embeddings blended
  * with the learned null features by the object mask -> fp16 [rows, Demb+64] (input of PositionNet.linears[0]). */
 int b200lmd_position_embed(const void* boxes, const void* masks, const void* emb, const void* null_pos,

@@ -195,6 +195,52 @@ extern "C" int b200lmd_position_embed(const void* boxes, const void* masks, cons
       (__half*)out_f16, rows, Demb)));
 }
 
+namespace b200 {
+// Device-side latent composition (utils/latents.py:37-83 compose_latents, after the per-box shifts of :85-118): every
+// output cell gathers from the per-box trajectory that owns it.
+//   lat     fp32 [S, BA, C, H, W]  all steps of the per-box generations (stays on the GPU after Phase A)
+//   owner   int32 [B, H, W]        1 + batch index (into BA) of the LAST box in composition order whose shifted mask
+//                                  covers the cell, 0 = background                       (latents.py:70-78)
+//   bowner  int32 [B, H, W]        same for the enlarged box masks that blend step 0 into the background (:62-68)
+//   shift   int32 [BA, 2]          integer (dx, dy) cell shift of each box: out[y, x] = lat[y - dy, x - dx], zero fill
+//   out     fp32 [S, B, C, H, W]   composed; step 0: bg -> box-mask layer -> mask layer, steps > 0: mask layer over zeros
+__global__ void compose_latents_kernel(const float* __restrict__ lat, const float* __restrict__ bg,
+                                       const int* __restrict__ owner, const int* __restrict__ bowner,
+                                       const int* __restrict__ shift, float* __restrict__ out, int S, int BA, int B, int C,
+                                       int H, int W) {
+  const long long total = (long long)S * B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int c = (int)((i / ((long long)W * H)) % C);
+    const int b = (int)((i / ((long long)W * H * C)) % B);
+    const int s = (int)(i / ((long long)W * H * C * B));
+    const int cell = (b * H + y) * W + x;
+    auto fetch = [&](int box) -> float {
+      const int sx = x - shift[2 * box], sy = y - shift[2 * box + 1];
+      if (sx < 0 || sx >= W || sy < 0 || sy >= H) return 0.f;
+      return lat[((((long long)s * BA + box) * C + c) * H + sy) * W + sx];
+    };
+    float v = 0.f;
+    const int o = owner[cell];
+    if (o > 0) v = fetch(o - 1);
+    else if (s == 0) {
+      const int bo = bowner[cell];
+      v = bo > 0 ? fetch(bo - 1) : bg[(((long long)b * C + c) * H + y) * W + x];
+    }
+    out[i] = v;
+  }
+}
+}  // namespace b200
+
+extern "C" int b200lmd_compose_latents(const void* lat, const void* bg, const int* owner, const int* bowner,
+                                       const int* shift, void* out, int S, int BA, int B, int C, int H, int W,
+                                       void* stream) {
+  B200_EW((compose_latents_kernel<<<ew_grid((long long)S * B * C * H * W), 256, 0, st>>>(
+      (const float*)lat, (const float*)bg, owner, bowner, shift, (float*)out, S, BA, B, C, H, W)));
+}
+
 // runtime switches (kept for A/B measurements of kernel generations; defaults are the fastest correct variants)
 extern "C" int b200lmd_set_option(const char* name, int value) {
   return b200::guarded([&] {

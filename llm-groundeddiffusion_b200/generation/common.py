@@ -14,8 +14,11 @@ import time
 import numpy as np
 import torch
 
+import ctypes
+
 from .. import latents as L
 from .. import pipelines as P
+from .._lib import check, cur_stream, lib, ptr
 from ..guidance import SampleLayout
 
 DEFAULT_SO_NEGATIVE_PROMPT = ("artifacts, blurry, smooth texture, bad quality, distortions, unrealistic, distorted image, "
@@ -206,7 +209,7 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
                          save_latents=True, fast_after_steps=fast_after_steps, dynamic_num_inference_steps=True)
         mark("phase A denoise")
         imgs = env.decode(resA["latents"])
-        la = resA["latents_all"].cpu()                         # [steps+1, BA, C, H, W]
+        la_dev = resA["latents_all"]                           # [steps+1, BA, C, H, W], stays on the GPU (f-2)
         tok_attn = None
         if sam_attn_start is not None:
             # utils/attn.py:9-38: mean over the saved steps [start:] then over heads, reshaped to the key's grid
@@ -219,26 +222,43 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
             so_imgs.append(img)
             masks_so.append(torch.as_tensor(env.refine_mask(
                 img, so_boxes[i], H, W, token_attn=tok_attn[i] if tok_attn is not None else None)).bool())
-            latents_all_so.append(la[:, i:i + 1])
+            latents_all_so.append(i)                                # index into la_dev's batch dimension
             saved_so.append([{k: st[k][i] for k in st} for st in resA["saved"]])     # per step {key: [heads, n]}
 
     mark("phase A outputs to host, masks")
-    # ------------------------------------------------------------------ composition (host bookkeeping)
+    # ------------------------------------------------------------------ composition
+    # host: integer bookkeeping only (mask centres -> cell shifts, ownership maps - like the loss tables);
+    # device: one gather kernel builds the composed latents of every image and step from the per-box trajectories
+    S_out = (steps if fast_after_steps is None else fast_after_steps) + 1
+    BA = len(owner)
+    shifts = np.zeros((max(BA, 1), 2), dtype=np.int32)
+    owner_maps = torch.zeros(B, H, W, dtype=torch.int32)
+    bowner_maps = torch.zeros(B, H, W, dtype=torch.int32)
     composed, frozen_masks, ref_maps, layouts, uncs, conds, glb, glp = [], [], [], [], [], [], [], []
     for b in range(B):
         idx = [i for i, o in enumerate(owner) if o == b] if latents_all_so else []
-        lat_b = [latents_all_so[i] for i in idx]
         msk_b = [masks_so[i] for i in idx]
         phrases = [p for p, _, _ in overall_pwb[b]]
         words = [w for _, w, _ in overall_pwb[b]]
         bboxes = [bx for _, _, bx in overall_pwb[b]]
         flat = [bx for group in bboxes for bx in group]
         offsets = [(0.0, 0.0)] * len(idx)
-        if align_with_overall_bboxes and lat_b:
-            lat_b, msk_b, offsets = L.align_to_boxes(lat_b, msk_b, flat, horizontal_only=horizontal_shift_only)
-        comp, fg_idx = L.compose(lat_b, msk_b, bg_latents[b], steps if fast_after_steps is None else fast_after_steps)
-        composed.append(comp)
-        frozen_masks.append((fg_idx != 0).float())
+        if align_with_overall_bboxes and idx:
+            # utils/latents.py:85-105 align_with_bboxes: mask centre -> box centre, in multiples of the coarsest grid
+            offsets, shifted = [], []
+            for m, box, gi in zip(msk_b, flat, idx):
+                cx, cy = L.mask_center(m)
+                dx = (box[0] + box[2]) / 2 - cx
+                dy = 0.0 if horizontal_shift_only else (box[1] + box[3]) / 2 - cy
+                offsets.append((dx, dy))
+                shifted.append(L.shift(m, dx, dy).bool())
+                shifts[gi] = L.shift_cells(dx, dy, H, W)
+            msk_b = shifted
+        if idx:
+            ow, bow = L.compose_owners([m.bool() for m in msk_b])
+            gidx = torch.tensor([0] + [i + 1 for i in idx], dtype=torch.int32)
+            owner_maps[b], bowner_maps[b] = gidx[ow.long()], gidx[bow.long()]
+        frozen_masks.append((owner_maps[b] != 0).float())
         pos, widx, prompt = env.phrase_indices(overall_prompts[b], phrases, words, add_suffix=True)
         unc, cnd = env.encode_prompts([prompt], ov_neg[b])
         uncs.append(unc)
@@ -277,8 +297,18 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
         gspec = P.GuidanceSpec(layouts=layouts, keys=keys, ref_ca_loss_weight=ref_ca_loss_weight,
                                ref_word_token_only=True, ref_maps=ref_maps if have_refs else None, **overall_guidance)
     gl = _gligen_inputs(env, glb, glp) if use_gligen else None
-    comp_all = torch.cat(composed, dim=1)                      # [steps+1, B, C, H, W]
-    mark("composition (host)")
+    bg_all = torch.cat(bg_latents, 0).to(net.dev, torch.float32).contiguous()          # [B, C, H, W]
+    comp_all = torch.empty(S_out, B, bg_all.shape[1], H, W, device=net.dev, dtype=torch.float32)
+    if BA:
+        check(lib().b200lmd_compose_latents(
+            ptr(la_dev), ptr(bg_all), ptr(owner_maps.to(net.dev)), ptr(bowner_maps.to(net.dev)),
+            ptr(torch.from_numpy(shifts).to(net.dev)), ptr(comp_all), ctypes.c_int(S_out), ctypes.c_int(BA),
+            ctypes.c_int(B), ctypes.c_int(bg_all.shape[1]), ctypes.c_int(H), ctypes.c_int(W), cur_stream()))
+        torch.cuda.current_stream().synchronize()      # the temporaries above must outlive the launch
+    else:
+        comp_all.zero_()
+        comp_all[0] = bg_all
+    mark("composition")
     resB = P.denoise(net, comp_all[0], torch.cat(uncs, 0), torch.cat(conds, 0), steps, guidance_scale=guidance_scale,
                      guidance=gspec, frozen_mask=torch.stack(frozen_masks, 0), frozen_latents=comp_all,
                      frozen_steps=frozen_steps, gligen=gl, gligen_beta=overall_beta)

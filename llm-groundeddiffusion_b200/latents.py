@@ -107,3 +107,25 @@ def compose(latents_all_list, masks, latents_bg, steps, compose_box_to_bg=True):
         mf = m[None, None, None].float()
         composed = composed * (1.0 - mf) + latents_all_list[i] * mf
     return composed, fg_idx
+
+
+def shift_cells(x_off, y_off, hh, ww, base=8):
+    """the integer cell shift shift() applies to a normalised offset (utils/utils.py:160-164)"""
+    return round(x_off * base) * (ww // base), round(y_off * base) * (hh // base)
+
+
+def compose_owners(masks):
+    """Ownership maps of compose_latents (utils/latents.py:56-78) for already-shifted masks[i] (bool [H, W]):
+    owner[y, x] = 1 + i of the last mask in composition order (largest first) covering the cell, bowner the same for the
+    enlarged box masks that blend step 0 into the background; 0 = none.  `owner` is the reference's
+    foreground_indices."""
+    H, W = masks[0].shape if masks else (0, 0)
+    owner = torch.zeros((H, W), dtype=torch.int32)
+    bowner = torch.zeros((H, W), dtype=torch.int32)
+    order = np.argsort(-np.array([float(m.sum()) for m in masks])) if masks else []
+    for i in order:
+        bm = mask_to_box_mask(masks[i]).bool()
+        bowner[bm] = int(i) + 1
+    for i in order:
+        owner[masks[i].bool()] = int(i) + 1
+    return owner, bowner

@@ -149,3 +149,33 @@ def test_lmd_run_tiny_fast_schedule_vs_reference(cuda):
 def test_lmd_run_config1_sd15_vs_reference(cuda):
     """BASELINE config 1 at full SD1.5 widths through lgd_b200.generation.lmd.run"""
     _check("config1", tol_final=0.1, tol_so=0.1)
+
+
+def test_device_composition_matches_host_mirror(cuda):
+    """b200lmd_compose_latents (gather by ownership map + per-box integer shift) vs the host mirror of
+    utils/latents.py compose_latents_with_alignment (lgd_b200.latents.compose / align_to_boxes, themselves compared with
+    the unmodified reference in tests/test_capi_and_host.py)"""
+    import ctypes
+    import lgd_b200.latents as L
+    from lgd_b200._lib import check, cur_stream, lib, ptr
+    g = torch.Generator().manual_seed(0)
+    S, H, W, C = 6, 64, 64, 4
+    boxes = [(0.1, 0.2, 0.5, 0.7), (0.45, 0.3, 0.95, 0.9), (0.3, 0.05, 0.6, 0.35)]
+    targets = [(0.2, 0.25, 0.6, 0.75), (0.4, 0.2, 0.9, 0.8), (0.05, 0.5, 0.35, 0.8)]
+    lat = [torch.randn(S, 1, C, H, W, generator=g) for _ in boxes]
+    masks = [L.box_to_mask(b, H, W).bool() for b in boxes]
+    bg = torch.randn(1, C, H, W, generator=g)
+    for horizontal in (False, True):
+        lat_s, msk_s, offs = L.align_to_boxes(lat, masks, targets, horizontal_only=horizontal)
+        ref, fg_idx = L.compose(lat_s, msk_s, bg, S - 1)
+        ow, bow = L.compose_owners([m.bool() for m in msk_s])
+        assert torch.equal(ow.long(), fg_idx)
+        shifts = torch.tensor([L.shift_cells(dx, dy, H, W) for dx, dy in offs], dtype=torch.int32)
+        lat_dev = torch.cat(lat, 1).to(cuda).contiguous()
+        out = torch.empty(S, 1, C, H, W, device=cuda)
+        check(lib().b200lmd_compose_latents(ptr(lat_dev), ptr(bg.to(cuda)), ptr(ow[None].contiguous().to(cuda)),
+                                            ptr(bow[None].contiguous().to(cuda)), ptr(shifts.to(cuda)), ptr(out),
+                                            ctypes.c_int(S), ctypes.c_int(3), ctypes.c_int(1), ctypes.c_int(C),
+                                            ctypes.c_int(H), ctypes.c_int(W), cur_stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), ref), (out.cpu() - ref).abs().max()
