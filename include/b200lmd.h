@@ -101,6 +101,16 @@ int b200lmd_latent_update(void* z, const void* grad, int ld_g, int B, int Cz, in
  * masks, like the loss tables); shift int32 [BA,2] = (dx, dy) cells.  lat fp32 [S,BA,C,H,W], out fp32 [S,B,C,H,W]. */
 int b200lmd_compose_latents(const void* lat, const void* bg, const int* owner, const int* bowner, const int* shift,
                             void* out, int S, int BA, int B, int C, int H, int W, void* stream);
+/* VAE decoder helpers (models/pipelines.py:117-127; diffusers 0.18 AutoencoderKL.decode - the convolutions, GroupNorms
+ * and the mid-block attention run on the conv / GN / GEMM entry points above):
+ *   vae_prepare_latents  post_quant_conv(z * inv_scale) (1x1, 4 -> 4) from fp32 NCHW latents to fp16 NHWC-8
+ *   softmax_rows         row softmax of fp32 scores [rows, n] -> fp16 probabilities (the single-head 512-wide mid-block
+ *                        attention is two GEMMs around it)
+ *   vae_to_uint8         round(clamp(x / 2 + 0.5, 0, 1) * 255) of the first 3 channels -> uint8 [pixels, 3] */
+int b200lmd_vae_prepare_latents(const void* z_f32, const void* pq_w, const void* pq_b, void* y_f16, int B, int HW,
+                                float inv_scale, void* stream);
+int b200lmd_softmax_rows(const void* scores_f32, void* probs_f16, long long rows, int n, void* stream);
+int b200lmd_vae_to_uint8(const void* x_f32, int ld, void* y_u8, long long pixels, void* stream);
 /* GLIGEN PositionNet front end (models/unet_2d_condition.py:63-114): Fourier box features + phrase embeddings blended
  * with the learned null features by the object mask -> fp16 [rows, Demb+64] (input of PositionNet.linears[0]). */
 int b200lmd_position_embed(const void* boxes, const void* masks, const void* emb, const void* null_pos,

@@ -241,6 +241,99 @@ extern "C" int b200lmd_compose_latents(const void* lat, const void* bg, const in
       (const float*)lat, (const float*)bg, owner, bowner, shift, (float*)out, S, BA, B, C, H, W)));
 }
 
+namespace b200 {
+// ---- VAE decoder helpers (models/pipelines.py:117-127 decode; diffusers 0.18 AutoencoderKL.decode)
+// latents fp32 NCHW [B, 4, HW] -> post_quant_conv (1x1, 4 -> 4, bias) of z * inv_scale -> fp16 NHWC-8 [B, HW, 8]
+__global__ void vae_prepare_latents_kernel(const float* __restrict__ z, const float* __restrict__ w /*[4][4]*/,
+                                           const float* __restrict__ bias /*[4]*/, __half* __restrict__ y, int B, int HW,
+                                           float inv_scale) {
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = z[(b * 4 + c) * HW + p] * inv_scale;
+    float f[8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) f[o] = bias[o] + w[o * 4] * v[0] + w[o * 4 + 1] * v[1] + w[o * 4 + 2] * v[2] + w[o * 4 + 3] * v[3];
+#pragma unroll
+    for (int o = 4; o < 8; ++o) f[o] = 0.f;
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(f);
+  }
+}
+// row softmax: fp32 scores [rows, n] (already scaled) -> fp16 probabilities [rows, n]; one block per row
+__global__ void softmax_rows_kernel(const float* __restrict__ s, __half* __restrict__ pr, long long rows, int n) {
+  __shared__ float red[32];
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* row = reinterpret_cast<const float4*>(s + r * n);
+    const int n4 = n >> 2;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 f = row[i];
+      m = fmaxf(fmaxf(m, fmaxf(f.x, f.y)), fmaxf(f.z, f.w));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    float l = 0.f;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 f = row[i];
+      l += __expf(f.x - m) + __expf(f.y - m) + __expf(f.z - m) + __expf(f.w - m);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    l = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) l += red[w];
+    const float inv = 1.f / l;
+    __half2* out = reinterpret_cast<__half2*>(pr + r * n);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 f = row[i];
+      out[2 * i] = __floats2half2_rn(__expf(f.x - m) * inv, __expf(f.y - m) * inv);
+      out[2 * i + 1] = __floats2half2_rn(__expf(f.z - m) * inv, __expf(f.w - m) * inv);
+    }
+    __syncthreads();
+  }
+}
+// decoder output fp32 NHWC [B*HW, ld] (first 3 channels) -> uint8 [B*HW, 3] = round(clamp(x / 2 + 0.5, 0, 1) * 255)
+__global__ void vae_to_uint8_kernel(const float* __restrict__ x, int ld, unsigned char* __restrict__ y, long long pixels) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels * 3;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / 3;
+    const int c = (int)(i - p * 3);
+    const float v = fminf(fmaxf(x[p * ld + c] * 0.5f + 0.5f, 0.f), 1.f);
+    y[i] = (unsigned char)rintf(v * 255.f);
+  }
+}
+}  // namespace b200
+
+extern "C" int b200lmd_vae_prepare_latents(const void* z_f32, const void* pq_w, const void* pq_b, void* y_f16, int B,
+                                           int HW, float inv_scale, void* stream) {
+  B200_EW((vae_prepare_latents_kernel<<<ew_grid((long long)B * HW), 256, 0, st>>>(
+      (const float*)z_f32, (const float*)pq_w, (const float*)pq_b, (__half*)y_f16, B, HW, inv_scale)));
+}
+extern "C" int b200lmd_softmax_rows(const void* scores_f32, void* probs_f16, long long rows, int n, void* stream) {
+  return b200::guarded([&] {
+    using namespace b200;
+    if (n % 8) throw std::runtime_error("softmax_rows: n must be a multiple of 8");
+    long long blocks = rows < (long long)kNumSMs * 16 ? rows : (long long)kNumSMs * 16;
+    softmax_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)scores_f32,
+                                                                             (__half*)probs_f16, rows, n);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+extern "C" int b200lmd_vae_to_uint8(const void* x_f32, int ld, void* y_u8, long long pixels, void* stream) {
+  B200_EW((vae_to_uint8_kernel<<<ew_grid(pixels * 3), 256, 0, st>>>((const float*)x_f32, ld, (unsigned char*)y_u8,
+                                                                    pixels)));
+}
+
 // runtime switches (kept for A/B measurements of kernel generations; defaults are the fastest correct variants)
 extern "C" int b200lmd_set_option(const char* name, int value) {
   return b200::guarded([&] {

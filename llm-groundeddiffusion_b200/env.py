@@ -28,8 +28,9 @@ def _seed_of(s):
 
 
 class SyntheticEnv:
-    def __init__(self, ctx_dim=768, T=77, latent_hw=(64, 64), cache_device=None):
+    def __init__(self, ctx_dim=768, T=77, latent_hw=(64, 64), cache_device=None, vae_decoder=None):
         self.ctx_dim, self.T = ctx_dim, T
+        self.vae_decoder = vae_decoder      # lgd_b200.vae.B200VAEDecoder (synthetic weights offline) or None
         self.latent_hw = latent_hw
         # cache_device set: embeddings are memoised ON the device (inputs resident in HBM);
         # unset: every call produces pinned host tensors that the path copies host->device itself.
@@ -87,7 +88,10 @@ class SyntheticEnv:
         return torch.stack([self._embed("phrase:" + p, 1)[0] for p in phrases])
 
     def decode(self, latents):
-        return None
+        """models/pipelines.py:117-127 on the B200 VAE decoder when one is configured: uint8 [B, 8H, 8W, 3] (host)"""
+        if self.vae_decoder is None:
+            return None
+        return self.vae_decoder.decode(latents).cpu().numpy()
 
     def refine_mask(self, image, box, H, W, token_attn=None):
         return box_to_mask(box, H, W).bool()
