@@ -292,6 +292,9 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mode-a", action="store_true")
+    ap.add_argument("--vae", type=int, default=int(os.environ.get("B200_BENCH_VAE", "0")),
+                    help="1: decode every per-box and overall generation with the B200 VAE decoder (synthetic weights) "
+                         "inside the timed step, as models/pipelines.py:233,461,591 do")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -340,6 +343,8 @@ def main():
         lat = torch.cat([o["latents"] for o in outs], 0)
         host = lat.cpu()                                  # device -> host read of the step's result
         io["d2h"] = host.numel() * host.element_size()
+        if outs[0].image is not None:                     # decoded pictures already crossed to the host in env.decode
+            io["d2h"] += sum(o.image.nbytes + sum(im.nbytes for im in o.so_img_list) for o in outs)
         st = outs[0]["guidance_state"]
         last["iters"] = [int(sum(it[b] for it in st.iters)) for b in range(len(outs))]
         return host
@@ -365,8 +370,14 @@ def main():
         ms = e0.elapsed_time(e1)
         return parallel.max_over_ranks(ms, dev), _lib.launch_count() - n0, clk.summary()
 
-    env_res = SyntheticEnv(cache_device=dev)       # inputs resident in HBM (memoised on device)
-    env_host = SyntheticEnv(cache_device=None)     # inputs produced on the host each call (pinned), copied inside
+    vae = None
+    if args.vae:
+        from lgd_b200.vae import B200VAEDecoder, VAEConfig
+        vae = B200VAEDecoder(VAEConfig(), Wt.synthetic_vae_weights(VAEConfig(), seed=0, device=dev), dev)
+        config["unit_note"] = ("an 'image' is the decoded uint8 512x512x3 picture: every per-box and overall generation "
+                               "ends in the B200 VAE decode (synthetic weights); CLIP / SAM are outside the measured path")
+    env_res = SyntheticEnv(cache_device=dev, vae_decoder=vae)    # inputs resident in HBM (memoised on device)
+    env_host = SyntheticEnv(cache_device=None, vae_decoder=vae)  # inputs produced on the host each call (pinned)
     for i in range(args.warmup):
         step(env_res)
         torch.cuda.synchronize()

@@ -46,9 +46,9 @@ class B200VAEDecoder(B200UNet):
                 sd[k[len("decoder."):]] = v
         # conv_out: pad the 3 output channels to 8 (zero rows) so the epilogue stores whole vectors
         co = sd["conv_out.weight"]
-        pad_w = torch.zeros(8, *co.shape[1:], dtype=co.dtype)
+        pad_w = co.new_zeros(8, *co.shape[1:])
         pad_w[:co.shape[0]] = co
-        pad_b = torch.zeros(8, dtype=co.dtype)
+        pad_b = co.new_zeros(8)
         pad_b[:co.shape[0]] = sd["conv_out.bias"]
         sd["conv_out.weight"], sd["conv_out.bias"] = pad_w, pad_b
         # fold to_v's bias into to_out's: P (V + 1 b_v^T) Wo^T + b_o = P V Wo^T + (Wo b_v + b_o)

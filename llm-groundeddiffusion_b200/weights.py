@@ -100,3 +100,53 @@ def synthetic_weights(cfg, seed=0, device="cpu", qk_gain=3.0):
                 scale *= 0.5
             w[name] = scale * rn(shape)
     return w
+
+
+def vae_parameter_shapes(cfg):
+    """diffusers-0.18 AutoencoderKL decoder side (post_quant_conv.*, decoder.*) for a lgd_b200.vae.VAEConfig"""
+    out = []
+    conv = lambda n, co, ci, k: out.extend([(n + ".weight", (co, ci, k, k)), (n + ".bias", (co,))])
+    norm = lambda n, c: out.extend([(n + ".weight", (c,)), (n + ".bias", (c,))])
+    lin = lambda n, o, i: out.extend([(n + ".weight", (o, i)), (n + ".bias", (o,))])
+
+    def res(n, ci, co):
+        norm(n + ".norm1", ci); conv(n + ".conv1", co, ci, 3); norm(n + ".norm2", co); conv(n + ".conv2", co, co, 3)
+        if ci != co:
+            conv(n + ".conv_shortcut", co, ci, 1)
+    rc = list(reversed(cfg.block_out_channels))
+    conv("post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
+    conv("decoder.conv_in", rc[0], cfg.latent_channels, 3)
+    res("decoder.mid_block.resnets.0", rc[0], rc[0])
+    a = "decoder.mid_block.attentions.0"
+    norm(a + ".group_norm", rc[0])
+    for n in (".to_q", ".to_k", ".to_v", ".to_out.0"):
+        lin(a + n, rc[0], rc[0])
+    res("decoder.mid_block.resnets.1", rc[0], rc[0])
+    ch = rc[0]
+    for i, co in enumerate(rc):
+        for j in range(cfg.layers_per_block + 1):
+            res(f"decoder.up_blocks.{i}.resnets.{j}", ch, co)
+            ch = co
+        if i < len(rc) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", ch, ch, 3)
+    norm("decoder.conv_norm_out", ch)
+    conv("decoder.conv_out", cfg.out_channels, ch, 3)
+    return out
+
+
+def synthetic_vae_weights(cfg, seed=0, device="cpu"):
+    """seeded decoder weights of the real shapes (no VAE checkpoint exists offline)"""
+    g = torch.Generator(device=device).manual_seed(seed)
+    rn = lambda shape: torch.randn(shape, generator=g, device=device)
+    w = {}
+    for name, shape in vae_parameter_shapes(cfg):
+        if "norm" in name.split(".")[-2] and name.endswith(".weight"):
+            w[name] = 1.0 + 0.1 * rn(shape)
+        elif name.endswith(".bias"):
+            w[name] = 0.05 * rn(shape)
+        else:
+            scale = 1.0 / math.sqrt(math.prod(shape[1:]))
+            if name.endswith(("conv2.weight", "to_out.0.weight")):
+                scale *= 0.5
+            w[name] = scale * rn(shape)
+    return w
