@@ -45,6 +45,7 @@ class DDIMSchedule:
         self.init_noise_sigma = 1.0
         self.num_inference_steps = None
         self.timesteps = None
+        self.sigmas = None       # set to an array to take the sigma branch of the guidance step (pipelines.py:60-61)
 
     def set_timesteps(self, n):
         self.num_inference_steps = n
@@ -167,6 +168,15 @@ def build_losses(net, spec: GuidanceSpec, index, H, W, dev):
     return out
 
 
+def guidance_step_scale(sched, index, t):
+    """models/pipelines.py:60-69: schedulers that carry `sigmas` (Euler / LMS family) scale the guidance step by
+    sigmas[index]**2, DDIM-style schedulers by sqrt(1 - alpha_bar_t) (classifier-guidance scaling)"""
+    sig = getattr(sched, "sigmas", None)
+    if sig is not None:
+        return float(sig[index]) ** 2
+    return float((1.0 - sched.alphas_cumprod[int(t)]) ** 0.5)
+
+
 def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spec: GuidanceSpec, state: GuidanceState,
                              objs=None, fuser_on=False, use_graphs=False):
     """models/pipelines.py:16-82, batched with per-image predicates.  z: device fp32 [B,4,H,W], updated in place."""
@@ -188,7 +198,7 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
         state.t_dev = torch.empty(B, device=z.device, dtype=torch.float32)
     t_dev = state.t_dev
     t_dev.fill_(float(t))
-    step_scale = float((1.0 - sched.alphas_cumprod[int(t)]) ** 0.5)
+    step_scale = guidance_step_scale(sched, index, t)
     while active.any():
         if losses is None:
             losses = state.losses = build_losses(net, spec, index, H, W, z.device)

@@ -203,3 +203,72 @@ def test_compose_and_align_match_reference():
         for a, b in zip(rm, mm):
             assert torch.equal(a, b)
         np.testing.assert_allclose(np.array(ro, dtype=np.float64), np.array(mo, dtype=np.float64), rtol=0, atol=1e-7)
+
+
+def test_boxdiff_tables_and_struct():
+    """integer artefacts of the BoxDiff tables (cell masks, corner masks, k = floor(count * P) without clamp) against a
+    direct restatement of utils/boxdiff.py:48-87, and the C-ABI struct sizes"""
+    from lgd_b200 import boxdiff as BD, guidance as G
+    from oracle import guidance_ref
+    assert BD.TERM_DTYPE.itemsize == 20
+    assert ctypes.sizeof(BD.BoxdiffC) == 256      # 16 + 7 pointers, 6 + 1 ints, 9 + 1 floats, tail padding
+    rng = random.Random(1)
+    for _ in range(50):
+        side = rng.choice([8, 16, 24])
+        lay = []
+        for b in range(2):
+            boxes = []
+            for _o in range(rng.randint(1, 3)):
+                w_, h_ = rng.uniform(0.35, 0.6), rng.uniform(0.35, 0.6)
+                x, y = rng.uniform(0, 1 - w_), rng.uniform(0, 1 - h_)
+                boxes.append([(x, y, x + w_, y + h_)])
+            lay.append(G.SampleLayout(boxes, [[1 + 2 * i, 2 + 2 * i] for i in range(len(boxes))]))
+        off, terms, masks, corner = BD.build_tables(lay, side, 0.2, 1)
+        assert off.tolist() == [0, 2 * len(lay[0].bboxes), 2 * (len(lay[0].bboxes) + len(lay[1].bboxes))]
+        ti = 0
+        for s in lay:
+            for o, obj in enumerate(s.bboxes):
+                m = torch.zeros(side, side)
+                cx, cy = torch.zeros(side), torch.zeros(side)
+                for box in obj:
+                    x0, y0, x1, y1 = guidance_ref.scale_proportion(box, side, side)
+                    m[y0:y1, x0:x1] = 1
+                    cx[max(x0 - 1, 0):min(x0 + 2, side)] = 1.
+                    cx[max(x1 - 1, 0):min(x1 + 2, side)] = 1.
+                    cy[max(y0 - 1, 0):min(y0 + 2, side)] = 1.
+                    cy[max(y1 - 1, 0):min(y1 + 2, side)] = 1.
+                for tok in s.object_positions[o]:
+                    t = terms[ti]
+                    assert t["tok"] == tok
+                    assert np.array_equal(masks[t["mask"]], m.reshape(-1).numpy().astype(np.uint8))
+                    assert np.array_equal(corner[t["corner"]], torch.cat([cx, cy]).numpy().astype(np.uint8))
+                    assert t["k_fg"] == int((m.sum() * 0.2).long()) and t["k_bg"] == int(((1 - m).sum() * 0.2).long())
+                    ti += 1
+    with pytest.raises(ValueError):
+        BD.build_tables([G.SampleLayout([[(0.1, 0.1, 0.2, 0.2)]], [[1]])], 16, 0.2, 1)
+
+
+def test_compose_owners_match_host_compose():
+    import lgd_b200.latents as L
+    g = torch.Generator().manual_seed(3)
+    for trial in range(10):
+        H = W = 64
+        boxes = [(0.1 + 0.05 * trial % 0.3, 0.2, 0.5, 0.7), (0.4, 0.3, 0.95, 0.9), (0.3, 0.05, 0.6, 0.35)]
+        masks = [L.box_to_mask(b, H, W).bool() for b in boxes]
+        lat = [torch.randn(3, 1, 4, H, W, generator=g) for _ in boxes]
+        _, fg_idx = L.compose(lat, masks, torch.randn(1, 4, H, W, generator=g), 2)
+        ow, bow = L.compose_owners(masks)
+        assert torch.equal(ow.long(), fg_idx)
+        assert int((bow > 0).sum()) >= int((ow > 0).sum())
+    assert L.shift_cells(0.26, -0.13, 64, 64) == (16, -8)
+
+
+def test_guidance_step_scale_branches():
+    """models/pipelines.py:60-69: sigmas[index]**2 when the scheduler carries sigmas, sqrt(1 - alpha_bar_t) otherwise"""
+    from lgd_b200.pipelines import DDIMSchedule, guidance_step_scale
+    s = DDIMSchedule()
+    s.set_timesteps(50)
+    t = int(s.timesteps[3])
+    assert abs(guidance_step_scale(s, 3, t) - float((1 - s.alphas_cumprod[t]) ** 0.5)) < 1e-12
+    s.sigmas = np.linspace(14.6, 0.0, 51)
+    assert abs(guidance_step_scale(s, 3, t) - float(s.sigmas[3]) ** 2) < 1e-12
