@@ -243,8 +243,10 @@ __device__ __forceinline__ float loss_ratio(const LossRaw<PERMAX>& q, const Loss
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
   }
-  const float a = sa / ss;
-  const float g0 = -2.f * P.w * (1.f - a) / ss * gscale;
+  // a column whose fp16 probabilities all underflowed to zero carries no information: the reference's fp16 path
+  // divides 0 by 0 there (NaN loss); here the term counts as a = 0 with zero gradient (stated deviations)
+  const float a = ss > 0.f ? sa / ss : 0.f;
+  const float g0 = ss > 0.f ? -2.f * P.w * (1.f - a) / ss * gscale : 0.f;
 #pragma unroll
   for (int j = 0; j < PERMAX; ++j)
     if (j < per && i0 + j < n) {

@@ -300,11 +300,15 @@ def layout_generation(specs, bg_seeds, fg_seed_starts, *, use_gligen, so_guidanc
     bg_all = torch.cat(bg_latents, 0).to(net.dev, torch.float32).contiguous()          # [B, C, H, W]
     comp_all = torch.empty(S_out, B, bg_all.shape[1], H, W, device=net.dev, dtype=torch.float32)
     if BA:
+        # locals keep the uploaded tables alive across the launch (a temporary passed to ptr() is freed - and its
+        # block reused by the next upload - before the kernel runs)
+        ow_dev, bow_dev = owner_maps.to(net.dev), bowner_maps.to(net.dev)
+        sh_dev = torch.from_numpy(shifts).to(net.dev)
         check(lib().b200lmd_compose_latents(
-            ptr(la_dev), ptr(bg_all), ptr(owner_maps.to(net.dev)), ptr(bowner_maps.to(net.dev)),
-            ptr(torch.from_numpy(shifts).to(net.dev)), ptr(comp_all), ctypes.c_int(S_out), ctypes.c_int(BA),
-            ctypes.c_int(B), ctypes.c_int(bg_all.shape[1]), ctypes.c_int(H), ctypes.c_int(W), cur_stream()))
-        torch.cuda.current_stream().synchronize()      # the temporaries above must outlive the launch
+            ptr(la_dev), ptr(bg_all), ptr(ow_dev), ptr(bow_dev), ptr(sh_dev), ptr(comp_all), ctypes.c_int(S_out),
+            ctypes.c_int(BA), ctypes.c_int(B), ctypes.c_int(bg_all.shape[1]), ctypes.c_int(H), ctypes.c_int(W),
+            cur_stream()))
+        torch.cuda.current_stream().synchronize()      # ... and until it has finished
     else:
         comp_all.zero_()
         comp_all[0] = bg_all

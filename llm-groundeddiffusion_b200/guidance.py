@@ -146,25 +146,29 @@ def build_key_tables(samples: Sequence[SampleLayout], slot_of, key, n, heads, n_
 
 
 class KeyLoss:
-    """device-resident loss tables + scratch of one attention key"""
+    """device-resident loss tables + scratch of one attention key.
+
+    Every device buffer is allocated ONCE at a fixed capacity and refilled in place by `update()`: their addresses are
+    baked into captured CUDA graphs (the b200lmd_xattn_loss struct travels by value in the kernel parameters), so a
+    graph captured for one batch of layouts is replayed for the next batch after an update - no re-capture."""
 
     def __init__(self, samples, slot_tok_dev, slot_of, key, n, heads, n_keys, params: LossParams, device, ext_ld=80,
-                 gscale=1.0):
+                 gscale=1.0, mask_rows=None, ref_rows=None):
         B = len(samples)
-        off, terms, masks, refs = build_key_tables(samples, slot_of, key, n, heads, n_keys, params)
         self.n, self.heads, self.B = n, heads, B
-        self.term_off = torch.from_numpy(off).to(device)
-        self.terms = torch.from_numpy(terms.view(np.uint8).reshape(-1).copy() if len(terms) else
-                                      np.zeros(TERM_DTYPE.itemsize, np.uint8)).to(device)
-        self.masks = torch.from_numpy(masks).to(device)
-        # reference maps live in ONE static device buffer (pointer baked into captured CUDA graphs); set_step() refills
-        # it in place.  Entries may be host arrays or device tensors (Phase-A maps stay on the GPU).
         self.key, self.device = key, device
-        self.ref_entries = refs
-        self.refs = torch.zeros(max(1, len(refs)), heads, n, device=device, dtype=torch.float32)
-        self.set_step(0)
-        self.slot_tok = slot_tok_dev
         max_slots = lib().b200lmd_max_loss_slots()
+        off, terms, masks, refs = build_key_tables(samples, slot_of, key, n, heads, n_keys, params)
+        self.cap_terms = B * 80
+        self.cap_masks = max(len(masks), mask_rows or B * 16)
+        self.cap_refs = max(len(refs), ref_rows or B * 8, 1)
+        self.term_off = torch.zeros(B + 1, dtype=torch.int32, device=device)
+        self.terms = torch.zeros(self.cap_terms * TERM_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        self.masks = torch.zeros(self.cap_masks, n, dtype=torch.uint8, device=device)
+        # reference maps live in ONE static device buffer; set_step() refills it in place.  Entries may be host arrays
+        # or device tensors (Phase-A maps stay on the GPU).
+        self.refs = torch.zeros(self.cap_refs, heads, n, device=device, dtype=torch.float32)
+        self.slot_tok = slot_tok_dev
         self.pcol = torch.zeros(B * heads, max_slots, n, device=device, dtype=torch.float32)
         self.counters = torch.zeros(B * heads, device=device, dtype=torch.int32)
         self.loss_part = torch.zeros(B * heads, device=device, dtype=torch.float32)
@@ -173,6 +177,31 @@ class KeyLoss:
                             self.refs.data_ptr(), self.slot_tok.data_ptr(), self.pcol.data_ptr(),
                             self.counters.data_ptr(), self.loss_part.data_ptr(), self.dp_extra.data_ptr(), ext_ld,
                             gscale, 1e-5)
+        self._fill(off, terms, masks, refs)
+
+    def fits(self, n_terms, n_masks, n_refs):
+        return n_terms <= self.cap_terms and n_masks <= self.cap_masks and n_refs <= self.cap_refs
+
+    def _fill(self, off, terms, masks, refs):
+        dev = self.device
+        self.term_off.copy_(torch.from_numpy(off))
+        if len(terms):
+            raw = torch.from_numpy(terms.view(np.uint8).reshape(-1).copy())
+            self.terms[:raw.numel()].copy_(raw)
+        self.masks[:masks.shape[0]].copy_(torch.from_numpy(masks))
+        self.ref_entries = refs
+        self.set_step(0)
+
+    def update(self, samples, slot_of, n_keys, params: LossParams):
+        """refill the static tables for a new batch of layouts (same B, key, resolution); returns False when the new
+        tables exceed the allocated capacity (the caller then builds a fresh KeyLoss and re-captures)"""
+        if len(samples) != self.B:
+            return False
+        off, terms, masks, refs = build_key_tables(samples, slot_of, self.key, self.n, self.heads, n_keys, params)
+        if not self.fits(len(terms), len(masks), len(refs)):
+            return False
+        self._fill(off, terms, masks, refs)
+        return True
 
     def set_step(self, index):
         """load the reference maps of denoising step `index` (utils/guidance.py:181) into the static buffer"""

@@ -42,7 +42,7 @@ def setup(batch=8, fuser=1, tiny=0):
         lay.append(G.SampleLayout(bx, pos, [p[-1] for p in pos]))
     spec = P.GuidanceSpec(layouts=lay, loss_scale=5, loss_threshold=0.0, max_iter=1, max_index_step=30, fg_weight=1.0,
                           bg_weight=4.0)
-    losses = P.build_losses(net, spec, 0, side, side, dev)
+    losses = P.build_losses(net, spec, 0, side, side, dev)[0]
     gl = dict(boxes=torch.rand(2 * B, 30, 4, generator=g), masks=(torch.rand(2 * B, 30, generator=g) > 0.8).float(),
               positive_embeddings=torch.randn(2 * B, 30, 768, generator=g))
     objs = net.position_net(gl["boxes"], gl["masks"], gl["positive_embeddings"])

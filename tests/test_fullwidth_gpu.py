@@ -77,8 +77,9 @@ def test_sd15_gligen_cfg_forward_matches_oracle(cuda, sd15):
     print("sd15+gligen eps rel-L2", r, "maps max abs", worst, "mean abs", mean)
     _note("sd15_gligen_cfg_forward", dict(eps_rel_l2=r, maps_max_abs=worst, maps_mean_abs=mean))
     assert len(saved) == 16
-    assert r < 2e-2, r
-    assert worst < 6e-2, worst
+    assert r < 5e-3, r              # measured 2.2e-3 (profiles/r2/fullwidth_parity.json)
+    assert worst < 6e-2, worst      # measured 3.4e-2 (single near-tie entries of nearly one-hot maps), mean 6.7e-5
+    assert mean < 2e-4, mean
 
 
 @pytest.mark.parametrize("fuser_on", [True, False])
@@ -130,8 +131,8 @@ def test_sd15_guidance_gradient_matches_oracle_autograd(cuda, sd15, fuser_on):
         r = _rel(grad[b:b + 1], gref)
         out[f"image{b}"] = dict(loss=float(loss[b]), loss_oracle=float(L), grad_rel_l2=r)
         print("sd15 guidance image", b, "loss", float(loss[b]), float(L), "grad rel-L2", r)
-        assert abs(float(loss[b]) - float(L)) < 2e-2 * abs(float(L)), (float(loss[b]), float(L))
-        assert r < 8e-2, r
+        assert abs(float(loss[b]) - float(L)) < 1e-3 * abs(float(L)), (float(loss[b]), float(L))   # measured 1.5e-4
+        assert r < 4e-2, r                                                                            # measured 1.7e-2
     _note(f"sd15_guidance_gradient_fuser_{int(fuser_on)}", out)
 
 
@@ -161,8 +162,8 @@ def test_sd21_forward_96_matches_oracle(cuda):
     worst = max(float((saved[k]["probs"].float().cpu() - ref_saved[k]).abs().max()) for k in ref_saved)
     print("sd21 96x96 eps rel-L2", r, "maps max abs", worst)
     _note("sd21_forward_96", dict(eps_rel_l2=r, maps_max_abs=worst))
-    assert r < 2e-2, r
-    assert worst < 6e-2, worst
+    assert r < 5e-3, r              # measured 2.0e-3
+    assert worst < 5e-2, worst      # measured 2.3e-2
 
 
 # ---------------------------------------------------------------------------------------------- kernel shapes the

@@ -15,11 +15,11 @@ def _rel(a, b):
     return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 
 
-def _net(gligen, seed=0):
+def _net(gligen, seed=0, qk_gain=3.0):
     from lgd_b200.unet import B200UNet, UNetConfig
     from oracle import unet_ref
     ocfg = unet_ref.UNetConfig.tiny(gligen=gligen)
-    w = unet_ref.make_weights(ocfg, seed=seed)
+    w = unet_ref.make_weights(ocfg, seed=seed, qk_gain=qk_gain)
     return ocfg, w, B200UNet(UNetConfig.tiny(gligen=gligen), w, "cuda:0")
 
 
@@ -28,7 +28,9 @@ def test_backward_guidance_plugin(cuda):
     from lgd_b200.generation import backward_guidance as plug, common
     from oracle import pipeline_ref
     import lgd_b200.latents as L
-    ocfg, w, net = _net(False, seed=2)
+    # milder attention than the other tests: with near-one-hot maps whole token columns underflow to zero in fp16 and
+    # the ratio sum(P M) / sum(P) is 0/0 (the reference's autocast path gives NaN there; ours counts the term as a = 0)
+    ocfg, w, net = _net(False, seed=2, qk_gain=1.0)
     env = SyntheticEnv()
     common.configure(net, env)
     steps = 4
@@ -46,9 +48,10 @@ def test_backward_guidance_plugin(cuda):
         tr = []
         ref = pipeline_ref.denoise(w, ocfg, L.seeded_noise([3, 5][b], 4, 32, 32), unc, cnd, steps, g=g, trace=tr)
         ours_iters = [it[b] for it in st.iters]
-        assert ours_iters == ref["iters"], (ours_iters, ref["iters"])
         first = next(t for t in st.trace if t[3][b])[2][b]
+        print("backward_guidance image", b, "first loss ours", first, "oracle", tr[0][2], "iters", ours_iters, ref["iters"])
         assert abs(first - tr[0][2]) < 1e-2 * abs(tr[0][2]), (first, tr[0][2])
+        assert ours_iters == ref["iters"], (ours_iters, ref["iters"])
         r = _rel(outs[b]["latents"].cpu(), ref["latents"])
         print("backward_guidance image", b, "iters", ours_iters, "final-latent rel-L2", r)
         assert r < 0.1, r

@@ -12,11 +12,11 @@ def _rel(a, b):
     return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 
 
-def _setup(gligen, B, side, seed=0):
+def _setup(gligen, B, side, seed=0, qk_gain=3.0):
     from lgd_b200.unet import B200UNet, UNetConfig
     from oracle import unet_ref
     ocfg = unet_ref.UNetConfig.tiny(gligen=gligen)
-    w = unet_ref.make_weights(ocfg, seed=seed)
+    w = unet_ref.make_weights(ocfg, seed=seed, qk_gain=qk_gain)
     net = B200UNet(UNetConfig.tiny(gligen=gligen), w, "cuda:0")
     g = torch.Generator().manual_seed(seed + 1)
     z = torch.randn(B, 4, side, side, generator=g)
@@ -46,12 +46,13 @@ def test_forward_matches_oracle(cuda):
         assert (saved[k]["probs"].float().cpu() - ref_saved[k]).abs().max() < 6e-2, k
 
 
-@pytest.mark.parametrize("with_ref", [False, True])
-def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref):
+@pytest.mark.parametrize("with_ref,ratio", [(False, False), (True, False), (False, True)])
+def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref, ratio):
     from lgd_b200 import guidance as G
     from oracle import guidance_ref, unet_ref
     B, side = 2, 32
-    ocfg, w, net, z, uncond, cond = _setup(False, B, side, seed=3)
+    # ratio-based energy: milder attention, so that no fp16 token column underflows to all-zero (0/0 in the ratio)
+    ocfg, w, net, z, uncond, cond = _setup(False, B, side, seed=3, qk_gain=1.0 if ratio else 3.0)
     kv = net.set_text(torch.cat([uncond, cond], 0))
     heads = 8
     g = torch.Generator().manual_seed(11)
@@ -66,7 +67,7 @@ def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref):
                       for k in KEYS} for _ in boxes] for boxes in bboxes]
         layouts.append(G.SampleLayout(bboxes, pos, words, refs))
     params = G.LossParams(loss_scale=5.0, fg_weight=1.0, bg_weight=4.0, ref_ca_loss_weight=2.0,
-                          ref_word_token_only=True, use_ref=with_ref)
+                          ref_word_token_only=True, use_ref=with_ref, use_ratio_based_loss=ratio)
     slot_tok, slot_of = G.assign_slots(layouts, params)
     slot_dev = torch.from_numpy(slot_tok).to(cuda)
     losses = {k: G.KeyLoss(layouts, slot_dev, slot_of, k, 16 if k[0] == "mid" else 64, heads, len(KEYS), params, cuda,
@@ -84,7 +85,8 @@ def test_guidance_gradient_matches_oracle_autograd(cuda, with_ref):
         if with_ref:
             refs = [[{k: torch.from_numpy(m[k]) for k in KEYS} for m in obj] for obj in layouts[b].ref_maps]
         L = guidance_ref.ca_loss({k: v[0] for k, v in saved.items()}, layouts[b].bboxes, layouts[b].object_positions,
-                                 KEYS, 0.2, 0.2, 1.0, 4.0, refs, layouts[b].word_token_indices, 2.0, True) * 5.0
+                                 KEYS, 0.2, 0.2, 1.0, 4.0, refs, layouts[b].word_token_indices, 2.0, True,
+                                 use_ratio_based_loss=ratio) * 5.0
         gref = torch.autograd.grad(L, [zz])[0]
         assert abs(float(loss[b]) - float(L)) < 2e-2 * abs(float(L)), (float(loss[b]), float(L))
         r = _rel(grad[b:b + 1], gref)
