@@ -159,7 +159,9 @@ def test_lmd_run_tiny_fast_schedule_vs_reference(cuda):
 
 def test_lmd_run_config1_sd15_vs_reference(cuda):
     """BASELINE config 1 at full SD1.5 widths through lgd_b200.generation.lmd.run"""
-    _check("config1", tol_final=0.3, tol_so=0.2)
+    # measured (profiles/r2/layout_parity_config1.json): iteration counts exact (35 per generation), per-box final latents
+    # 5.1e-3 / 5.5e-3, overall final latents 1.55e-2 after 105 guidance iterations, loss traces within 1.3e-3
+    _check("config1", tol_final=0.035, tol_so=0.012)
 
 
 def test_device_composition_matches_host_mirror(cuda):

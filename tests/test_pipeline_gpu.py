@@ -49,13 +49,13 @@ def test_semantic_guidance_loop(cuda):
         print("image", b, "final-latent rel-L2", r, "oracle loss", ref["loss"], "ours", res["state"].loss[b])
         # fp16 path vs fp32 oracle after several large guidance steps; top-k membership near ties differs between
         # fp16 and fp32 maps (the autocast reference has the same sensitivity), so the bound is loose
-        assert r < 0.15, r
+        assert r < 0.1, r            # measured 4.8e-2 / 5.0e-2 (large scale-10 guidance steps on the small topology)
         # the first loss evaluation starts from identical latents: tight; the final one has gone through all guidance
         # updates (discrete top-k membership amplifies fp16-vs-fp32 differences): loose
         first_ours, first_ref = res["state"].trace[0][2][b], tr[0][2]
         print("first loss ours", first_ours, "oracle", first_ref)
         assert abs(first_ours - first_ref) < 1e-2 * abs(first_ref)
-        assert abs(res["state"].loss[b] - ref["loss"]) < 0.15 * abs(ref["loss"])
+        assert abs(res["state"].loss[b] - ref["loss"]) < 0.05 * abs(ref["loss"])   # measured 5e-4 / 2e-2
         for si, (s_ref, s) in enumerate(zip(ref["saved"], res["saved"])):
             for k in s_ref:
                 # random-weight attention is nearly one-hot, so a near-tie that flips moves single entries by ~1:
@@ -102,8 +102,8 @@ def test_gligen_ref_frozen_loop(cuda):
         print("image", b, "final-latent rel-L2", r, "oracle loss", ref["loss"], "ours", res["state"].loss[b])
         # fp16 path vs fp32 oracle after several large guidance steps; top-k membership near ties differs between
         # fp16 and fp32 maps (the autocast reference has the same sensitivity), so the bound is loose
-        assert r < 0.15, r
-        assert abs(res["state"].loss[b] - ref["loss"]) < 0.15 * abs(ref["loss"])
+        assert r < 0.15, r           # measured 3.5e-2 / 7.8e-2
+        assert abs(res["state"].loss[b] - ref["loss"]) < 0.05 * abs(ref["loss"])   # measured 5e-4 / 6e-3
 
 
 def test_fast_schedule_loop(cuda):
@@ -128,7 +128,7 @@ def test_fast_schedule_loop(cuda):
                                    fast_rate=2, dynamic_num_inference_steps=True)
         r = _rel(res["latents"][b:b + 1].cpu(), ref["latents"])
         print("image", b, "final-latent rel-L2", r)
-        assert r < 2e-2, r
+        assert r < 1e-2, r           # measured 4.4e-3 / 4.5e-3
         assert _rel(res["latents_all"][:, b:b + 1].cpu(), ref["latents_all"]) < 2e-2
 
 
@@ -163,5 +163,5 @@ def test_v_prediction_guidance_loop(cuda):
         assert list(iters[b]) == ref["iters"], (iters[b], ref["iters"])
         r = _rel(res["latents"][b:b + 1].cpu(), ref["latents"])
         print("image", b, "final-latent rel-L2", r, "oracle loss", ref["loss"], "ours", res["state"].loss[b])
-        assert r < 0.15, r
-        assert abs(res["state"].loss[b] - ref["loss"]) < 0.15 * abs(ref["loss"])
+        assert r < 0.04, r           # measured 1.6e-2 / 1.7e-2
+        assert abs(res["state"].loss[b] - ref["loss"]) < 0.02 * abs(ref["loss"])   # measured 7e-4 / 2.5e-3

@@ -30,9 +30,9 @@ def test_vae_decode_matches_oracle(cuda, name, B, side):
     got = raw[..., :3].permute(0, 3, 1, 2).cpu()
     r = _rel(got, ref)
     print(name, side, "decoder output rel-L2", r)
-    assert r < 2e-2, r
+    assert r < 5e-3, r            # measured 1.2e-3 .. 1.6e-3
     ref_u8 = vae_ref.to_uint8(ref)
     assert img.shape == (B, 8 * side, 8 * side, 3) and img.dtype == torch.uint8
     d = np.abs(img.cpu().numpy().astype(np.int32) - ref_u8.astype(np.int32))
     print("uint8 max / mean abs diff", d.max(), d.mean())
-    assert d.mean() < 1.0 and d.max() <= 12
+    assert d.mean() < 0.2 and d.max() <= 2      # measured: max 1, mean 0.07 (rounding of values at .5)
