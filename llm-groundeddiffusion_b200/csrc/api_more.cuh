@@ -341,6 +341,7 @@ extern "C" int b200lmd_set_option(const char* name, int value) {
     if (n == "attn_v2") b200::attn_use_v2() = value != 0;
     else if (n == "gemm_v2") b200::gemm_use_v2() = value != 0;
     else if (n == "gemm_v3") b200::gemm_use_v3() = value != 0;
+    else if (n == "fused_loss_stage") b200::fused_loss_stage() = value != 0;
     else throw std::runtime_error("unknown option " + n);
   });
 }

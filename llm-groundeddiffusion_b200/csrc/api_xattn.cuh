@@ -79,6 +79,10 @@ extern "C" int b200lmd_xattn_fwd_f16(const void* q, const void* k, const void* v
 extern "C" int b200lmd_max_loss_slots(void) { return b200::kMaxSlots; }
 
 namespace b200 {
+inline bool& fused_loss_stage() {
+  static bool on = true;
+  return on;
+}
 inline unsigned long long*& fused_dbg() {
   static unsigned long long* p = nullptr;
   return p;
@@ -170,6 +174,7 @@ extern "C" int b200lmd_xattn_fused_f16(const void* x, const void* wq, const void
     p.has_loss = loss != nullptr;
     if (loss) p.L = *reinterpret_cast<const XattnLoss*>(loss);
     p.dbg = fused_dbg();
+    p.loss_stage = fused_loss_stage() ? 1 : 0;
     // per-row-tile arrival counters live right behind the scratch rows of o_scratch's owner: a small static buffer
     const int n_tiles = (int)(M / 128);
     if (2 * n_tiles + 16 * B > kFusedFlagInts || n_tiles * 8 > kFusedPartials)

@@ -204,19 +204,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld_x32(taddr + 64 + half * 32, gg);
           tmem_ld_wait();
           uint32_t o[16], pv[16], pg[16];
-          float bv[32], bg[32];                  // bias of this thread's 32 value / 32 gate columns (16-byte loads)
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 x4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + half * 32) + q4) : z4;
-            const float4 y4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 64 + half * 32) + q4) : z4;
-            bv[4 * q4] = x4.x; bv[4 * q4 + 1] = x4.y; bv[4 * q4 + 2] = x4.z; bv[4 * q4 + 3] = x4.w;
-            bg[4 * q4] = y4.x; bg[4 * q4 + 1] = y4.y; bg[4 * q4 + 2] = y4.z; bg[4 * q4 + 3] = y4.w;
-          }
+          // scalar __ldg bias reads (L1-resident, two per output): the 16-byte variant holds 64 more live registers
+          // in front of the erf-GELU and measured 9-15 % slower on the three GEGLU shapes (profiles/r2/ops_profile.txt)
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a0 = __uint_as_float(vv[2 * j]) + bv[2 * j], a1 = __uint_as_float(vv[2 * j + 1]) + bv[2 * j + 1];
-            const float g0 = __uint_as_float(gg[2 * j]) + bg[2 * j], g1 = __uint_as_float(gg[2 * j + 1]) + bg[2 * j + 1];
+            float a0 = __uint_as_float(vv[2 * j]), a1 = __uint_as_float(vv[2 * j + 1]);
+            float g0 = __uint_as_float(gg[2 * j]), g1 = __uint_as_float(gg[2 * j + 1]);
+            if (p.bias) {
+              a0 += __ldg(p.bias + n0 + half * 32 + 2 * j);
+              a1 += __ldg(p.bias + n0 + half * 32 + 2 * j + 1);
+              g0 += __ldg(p.bias + n0 + 64 + half * 32 + 2 * j);
+              g1 += __ldg(p.bias + n0 + 64 + half * 32 + 2 * j + 1);
+            }
             o[j] = pack_h2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
             pv[j] = pack_h2(a0, a1);
             pg[j] = pack_h2(g0, g1);

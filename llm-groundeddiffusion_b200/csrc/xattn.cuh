@@ -101,6 +101,13 @@ struct LossProb {      // decoded problem
   const float* R;      // nullptr for energy problems
   int tok, side, k;    // side: 0 fg top-k, 1 bg top-k, 2 ratio-based energy
   float w;
+  bool staged;         // src / mk point into shared memory (staged copy) instead of global memory
+};
+
+// staged copy of one (image, head)'s loss inputs in shared memory: the used pcol rows and one mask row per term
+struct LossStaged {
+  const float* col;    // [n_slots][n] or nullptr
+  const uint8_t* mk;   // [n_terms][n]
 };
 
 template <int PERMAX>
@@ -114,7 +121,7 @@ __device__ __forceinline__ void loss_load(LossRaw<PERMAX>& q, const LossProb& P,
     q.r[j] = 0.f;
     if (j < per && i < n) {
       const uint8_t mb = P.mk[i];
-      q.v[j] = __ldcg(P.src + i);
+      q.v[j] = P.staged ? P.src[i] : __ldcg(P.src + i);
       if (P.R) q.r[j] = P.R[i];
       if (mb) q.m |= 1ull << j;
     }
@@ -259,12 +266,14 @@ __device__ __forceinline__ float loss_ratio(const LossRaw<PERMAX>& q, const Loss
 constexpr int kLossScratchBytes = 160 * 4 + 160 * 2 + kMaxSlots * 4 + 16 + kMaxTerms * (int)sizeof(LossTerm);
 
 __device__ __forceinline__ LossProb loss_decode(const XattnLoss& L, const LossTerm* sterms, const int* stok,
-                                                unsigned short code, int bh, int h, int heads, int n) {
+                                                unsigned short code, int bh, int h, int heads, int n,
+                                                const LossStaged& stg) {
   const LossTerm& T = sterms[code >> 1];
   const int sub = code & 1;
   LossProb P;
-  P.src = L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
-  P.mk = L.masks + (long long)T.mask * n;
+  P.staged = stg.col != nullptr;
+  P.src = P.staged ? stg.col + (long long)T.slot * n : L.pcol + ((long long)bh * kMaxSlots + T.slot) * n;
+  P.mk = P.staged ? stg.mk + (long long)(code >> 1) * n : L.masks + (long long)T.mask * n;
   P.tok = stok[T.slot];
   if (T.type == 0) {
     P.R = nullptr;
@@ -289,9 +298,9 @@ template <int PERMAX, bool PIPE>
 __device__ __forceinline__ void loss_problem_loop(const XattnLoss& L, const LossTerm* sterms, const int* stok,
                                                   const unsigned short* pcode, float* prob_loss, float* dpx, int n_prob,
                                                   int first, int stride, int lane, int bh, int h, int heads, int n,
-                                                  int per) {
+                                                  int per, const LossStaged& stg) {
   if (first >= n_prob) return;
-  LossProb P = loss_decode(L, sterms, stok, pcode[first], bh, h, heads, n);
+  LossProb P = loss_decode(L, sterms, stok, pcode[first], bh, h, heads, n, stg);
   LossRaw<PERMAX> cur;
   loss_load(cur, P, n, per, lane);
   for (int pid = first; pid < n_prob; pid += stride) {
@@ -299,7 +308,7 @@ __device__ __forceinline__ void loss_problem_loop(const XattnLoss& L, const Loss
     LossProb Pn = P;
     LossRaw<PERMAX> nxt;
     if (PIPE && more) {                                    // next problem's loads fly during this problem's compute
-      Pn = loss_decode(L, sterms, stok, pcode[pid + stride], bh, h, heads, n);
+      Pn = loss_decode(L, sterms, stok, pcode[pid + stride], bh, h, heads, n, stg);
       loss_load(nxt, Pn, n, per, lane);
     }
     const float contrib = P.R ? loss_ref(cur, P, dpx, L.ext_ld, lane, per, L.eps, L.gscale)
@@ -311,7 +320,7 @@ __device__ __forceinline__ void loss_problem_loop(const XattnLoss& L, const Loss
         cur = nxt;
         P = Pn;
       } else {
-        P = loss_decode(L, sterms, stok, pcode[pid + stride], bh, h, heads, n);
+        P = loss_decode(L, sterms, stok, pcode[pid + stride], bh, h, heads, n, stg);
         loss_load(cur, P, n, per, lane);
       }
     }
@@ -371,7 +380,13 @@ __device__ __forceinline__ void loss_stage(const XattnLoss& L, float* scratch, i
       if (first + sub < 160) S.pcode[first + sub] = (unsigned short)(t * 2 + sub);
     n_prob += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (tid == 0) *S.n_prob = min(n_prob, 160);
+  if (tid == 0) {
+    S.n_prob[0] = min(n_prob, 160);
+    S.n_prob[1] = nterms;
+    int ns = 0;
+    while (ns < kMaxSlots && S.stok[ns] >= 0) ++ns;
+    S.n_prob[2] = ns;
+  }
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
@@ -387,19 +402,44 @@ __device__ __forceinline__ void loss_zero(const XattnLoss& L, int bh, int n, int
 // does not depend on arrival order.  done[bh] must be zero on entry and is zero again on exit (so is ready[bh]).
 __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int tid, int h, int heads, int bh, int n,
                                          int part, int nparts, float* partials, int* done,
-                                         unsigned long long* dbg = nullptr, int* ready = nullptr) {
+                                         unsigned long long* dbg = nullptr, int* ready = nullptr,
+                                         uint8_t* stage = nullptr, int stage_bytes = 0) {
   const int warp = tid >> 5, lane = tid & 31;
   LossScratch S = loss_scratch(scratch);
-  const int n_prob = *S.n_prob;
+  const int n_prob = S.n_prob[0];
   float* dpx = L.dp_extra + (long long)bh * n * L.ext_ld;
   const int per = (n + 31) >> 5;
   LOSS_STAMP(0);
+  // Stage the inputs of every problem of this (image, head) in shared memory with ONE cooperative pass of 16-byte
+  // loads (the used pcol rows are contiguous; one mask row per term), so the per-problem loads hit shared memory
+  // instead of paying an L2 round trip each under the phase-2 TMA traffic.
+  LossStaged stg;
+  stg.col = nullptr;
+  stg.mk = nullptr;
+  if (stage) {
+    const int nterms = S.n_prob[1], nslots = S.n_prob[2];
+    const int col_bytes = nslots * n * 4;
+    if ((n & 15) == 0 && col_bytes + nterms * n <= stage_bytes) {
+      float4* dcol = reinterpret_cast<float4*>(stage);
+      const float4* scol = reinterpret_cast<const float4*>(L.pcol + (long long)bh * kMaxSlots * n);
+      for (int i = tid; i < (col_bytes >> 4); i += 128) dcol[i] = __ldcg(scol + i);
+      uint4* dmk = reinterpret_cast<uint4*>(stage + col_bytes);
+      const int mvec = n >> 4;
+      for (int i = tid; i < nterms * mvec; i += 128) {
+        const int t = i / mvec, v = i - t * mvec;
+        dmk[i] = __ldg(reinterpret_cast<const uint4*>(L.masks + (long long)S.sterms[t].mask * n) + v);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      stg.col = reinterpret_cast<const float*>(stage);
+      stg.mk = stage + col_bytes;
+    }
+  }
   if (per <= 8)
     loss_problem_loop<8, true>(L, S.sterms, S.stok, S.pcode, S.prob_loss, dpx, n_prob, part * 4 + warp, 4 * nparts,
-                               lane, bh, h, heads, n, per);
+                               lane, bh, h, heads, n, per, stg);
   else
     loss_problem_loop<40, false>(L, S.sterms, S.stok, S.pcode, S.prob_loss, dpx, n_prob, part * 4 + warp, 4 * nparts,
-                                 lane, bh, h, heads, n, per);
+                                 lane, bh, h, heads, n, per, stg);
   LOSS_STAMP(1);
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (tid == 0) {                                          // fixed summation order => deterministic loss
@@ -409,6 +449,14 @@ __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int
     if (nparts == 1) {
       L.loss_part[bh] = acc;
       if (ready) ready[bh] = 0;                            // hand-shake counters end the launch at zero
+    } else if (nparts == 2) {
+      // two parts: loss_part[bh] was zeroed by part 0 before the hand-shake; 0 + a + b is the same float in either
+      // arrival order, so two fire-and-forget atomics replace the store / fence / ticket / re-read chain
+      atomicAdd(L.loss_part + bh, acc);
+      if (atomicAdd(done + bh, 1) == 1) {
+        done[bh] = 0;                                      // both parts are past their wait on `ready` by now
+        if (ready) ready[bh] = 0;
+      }
     } else {
       __stcg(partials + bh * nparts + part, acc);
       __threadfence();

@@ -38,7 +38,9 @@ struct FusedXattnParams {
   int* bh_done;              // [B*8] zero on entry: row tiles of an (image, head) that finished their loss share
   float* loss_partials;      // [B*8][tiles_per_img]
   unsigned long long* dbg;   // optional [grid][8] %globaltimer stamps (phase timeline), null in production
+  int loss_stage;            // 1: stage the loss inputs in shared memory (default), 0: per-problem global loads (A/B)
 };
+__device__ __forceinline__ bool fused_loss_stage_enabled(const FusedXattnParams& p) { return p.loss_stage != 0; }
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -245,6 +247,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // CTA's atomics by the publish fence below), term / slot tables and the problem list staged in shared memory
     if (p.has_loss) {
       loss_zero(p.L, bh, p.n, tok0, 128, tid);
+      if (p.tiles_per_img == 2 && tok0 == 0 && tid == 0) p.L.loss_part[bh] = 0.f;   // two-part combine adds into it
       loss_stage(p.L, sL, tid, b);
     }
     // ---- Q_h: TMEM -> fp16 -> smem A operand (and the optional Q slab for the backward)
@@ -475,8 +478,12 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         __threadfence();
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // staging area: the K/V region behind the residual / output staging rows (dead since the core)
+      uint8_t* lstage = sK + 128 * OLD * 2;
+      const int lstage_bytes = Cfg::K_BYTES + Cfg::V_BYTES - 128 * OLD * 2;
       loss_run(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, p.loss_partials, p.bh_done,
-               p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr, p.bh_ready);
+               p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr, p.bh_ready,
+               fused_loss_stage_enabled(p) ? lstage : nullptr, lstage_bytes);
     }
     if (p.residual) {
       asm volatile("cp.async.wait_all;" ::: "memory");

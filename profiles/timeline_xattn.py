@@ -13,7 +13,8 @@ from lgd_b200._lib import lib  # noqa: E402
 
 dev = torch.device("cuda:0")
 dbg = torch.zeros(128 * 16, dtype=torch.int64, device=dev)
-for wl in (False, True):
+for wl, stage in ((False, 1), (True, 0), (True, 1)):
+    lib().b200lmd_set_option(b"fused_loss_stage", ctypes.c_int(stage))
     dbg.zero_()
     lib().b200lmd_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
     r = bench.xattn_roofline(dev, with_loss=wl)
@@ -22,7 +23,7 @@ for wl in (False, True):
     t0 = t[:, 0].min()
     names = ["start", "Q acc done", "S done", "O done", "pre-sync2", "post-sync2", "out acc done", "end",
              "loss run", "loss probs", "loss end"]
-    print("with_loss", wl, "ms_per_op", r["ms_per_op"])
+    print("with_loss", wl, "loss inputs staged in smem", bool(stage), "ms_per_op", r["ms_per_op"], "frac", r["frac"])
     for i, nme in enumerate(names):
         col = t[:, i]
         col = col[col > 0]
