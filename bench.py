@@ -292,7 +292,10 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mode-a", action="store_true")
-    ap.add_argument("--vae", type=int, default=int(os.environ.get("B200_BENCH_VAE", "0")),
+    ap.add_argument("--workload", default="lmd_plus", choices=["lmd_plus", "backward_guidance_sd21", "boxdiff"],
+                    help="lmd_plus = BASELINE config 2 (the headline, default); backward_guidance_sd21 = config 3 (SD2.1 "
+                         "shapes, 768x768, v-prediction, batch 4); boxdiff = config 4 (SD1.5, 25 guided steps, batch 8)")
+    ap.add_argument("--vae", type=int, default=int(os.environ.get("B200_BENCH_VAE", "1")),
                     help="1: decode every per-box and overall generation with the B200 VAE decoder (synthetic weights) "
                          "inside the timed step, as models/pipelines.py:233,461,591 do")
     args = ap.parse_args()
@@ -323,7 +326,18 @@ def main():
     import torch.distributed as dist
     parallel.init("nccl", dev)
     pin = parallel.pin_host_threads(local, min(world, torch.cuda.device_count()))
-    cfg = UNetConfig.sd15(gligen=True)
+    wl = args.workload
+    cfg = {"lmd_plus": UNetConfig.sd15(gligen=True), "backward_guidance_sd21": UNetConfig.sd21(),
+           "boxdiff": UNetConfig.sd15()}[wl]
+    if wl == "backward_guidance_sd21":
+        if args.batch == 8:
+            args.batch = 4
+        config.update(workload="backward guidance (ratio energy) SD2.1 shapes 768x768 v-prediction, 50 steps, 5 guidance "
+                               "iterations x 10 steps, 4 boxes/prompt, 4 prompts/GPU (BASELINE config 3)",
+                      guidance="overall_loss_threshold=0: fixed 5 x 10 = 50 guidance iterations per image")
+    elif wl == "boxdiff":
+        config.update(workload="BoxDiff SD1.5 512x512, 50 steps, 25 guided steps x 1 iteration, 4 boxes/prompt, 8 "
+                               "prompts/GPU (BASELINE config 4)", guidance="fixed 25 BoxDiff steps per image")
     # the only collective on the path: start-up NCCL broadcast of the frozen weights from rank 0
     w = parallel.broadcast_weights(Wt.parameter_shapes(cfg), lambda: Wt.synthetic_weights(cfg, seed=0, device=dev), dev)
     log("weights ready")
@@ -339,14 +353,25 @@ def main():
     def step(env, fixed=True):
         common.configure(net, env)
         kw = dict(overall_loss_threshold=0.0) if fixed else {}
-        outs = lmd_plus.run_batch(specs, seeds, fgs, num_inference_steps=args.denoise_steps, return_latents=True, **kw)
+        if wl == "lmd_plus":
+            outs = lmd_plus.run_batch(specs, seeds, fgs, num_inference_steps=args.denoise_steps, return_latents=True, **kw)
+        elif wl == "backward_guidance_sd21":
+            from lgd_b200.generation import backward_guidance
+            outs = backward_guidance.run_batch(specs, seeds, num_inference_steps=args.denoise_steps, height=768, width=768,
+                                               prediction_type="v_prediction", return_latents=True, **kw)
+        else:
+            from lgd_b200.generation import boxdiff as boxdiff_plugin
+            outs = boxdiff_plugin.run_batch(specs, seeds, num_inference_steps=args.denoise_steps, return_latents=True)
         lat = torch.cat([o["latents"] for o in outs], 0)
         host = lat.cpu()                                  # device -> host read of the step's result
         io["d2h"] = host.numel() * host.element_size()
         if outs[0].image is not None:                     # decoded pictures already crossed to the host in env.decode
             io["d2h"] += sum(o.image.nbytes + sum(im.nbytes for im in o.so_img_list) for o in outs)
         st = outs[0]["guidance_state"]
-        last["iters"] = [int(sum(it[b] for it in st.iters)) for b in range(len(outs))]
+        if wl == "boxdiff":
+            last["iters"] = [len(getattr(st, "boxdiff_losses", []))] * len(outs)
+        else:
+            last["iters"] = [int(sum(it[b] for it in st.iters)) for b in range(len(outs))]
         return host
 
     def barrier():
@@ -371,13 +396,14 @@ def main():
         return parallel.max_over_ranks(ms, dev), _lib.launch_count() - n0, clk.summary()
 
     vae = None
+    ctx_dim = cfg.cross_attention_dim
     if args.vae:
         from lgd_b200.vae import B200VAEDecoder, VAEConfig
         vae = B200VAEDecoder(VAEConfig(), Wt.synthetic_vae_weights(VAEConfig(), seed=0, device=dev), dev)
         config["unit_note"] = ("an 'image' is the decoded uint8 512x512x3 picture: every per-box and overall generation "
                                "ends in the B200 VAE decode (synthetic weights); CLIP / SAM are outside the measured path")
-    env_res = SyntheticEnv(cache_device=dev, vae_decoder=vae)    # inputs resident in HBM (memoised on device)
-    env_host = SyntheticEnv(cache_device=None, vae_decoder=vae)  # inputs produced on the host each call (pinned)
+    env_res = SyntheticEnv(ctx_dim=ctx_dim, cache_device=dev, vae_decoder=vae)    # inputs resident in HBM
+    env_host = SyntheticEnv(ctx_dim=ctx_dim, cache_device=None, vae_decoder=vae)  # inputs produced on the host (pinned)
     for i in range(args.warmup):
         step(env_res)
         torch.cuda.synchronize()
@@ -390,14 +416,17 @@ def main():
     log(f"timed (host inputs, e2e): {ms_e2e:.1f} ms")
     io["h2d"] = env_host.bytes_out // max(1, args.steps)
     imgs = args.batch * world * args.steps
-    line = {"metric": "images/sec (LMD+ SD1.5, 50 steps, 512^2)", "value": imgs / (ms * 1e-3), "unit": "images/s",
+    metric = {"lmd_plus": "images/sec (LMD+ SD1.5, 50 steps, 512^2)",
+              "backward_guidance_sd21": "images/sec (backward guidance SD2.1 shapes, 50 steps, 768^2)",
+              "boxdiff": "images/sec (BoxDiff SD1.5, 50 steps, 512^2)"}[wl]
+    line = {"metric": metric, "value": imgs / (ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": config, "clocks": clocks, "gpu_launches": launches,
             "guidance_iterations_per_image": iters_b, "host_threads": pin,
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": io["h2d"],
                     "d2h_bytes_per_step": io["d2h"]}}
-    if not args.no_mode_a:
+    if not args.no_mode_a and wl == "lmd_plus":
         step(env_res, fixed=False)                  # graphs / tables of the data-dependent variant
         ms_a, _, _ = timed(env_res, 1, fixed=False)
         line["mode_a"] = {"value": args.batch * world / (ms_a * 1e-3), "unit": "images/s", "ms_per_step": ms_a,
@@ -405,10 +434,10 @@ def main():
                           "note": "reference thresholds (overall_loss_threshold 5.0): data-dependent iteration counts"}
         log(f"timed (mode A): {ms_a:.1f} ms")
     if rank == 0:
-        if not args.no_roofline:
+        if not args.no_roofline and wl == "lmd_plus":
             line["roofline"] = xattn_roofline(dev)
             log("roofline micro-benchmark done")
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and wl == "lmd_plus":
             line["cpu_baseline"] = cpu_baseline()
             log("cpu baseline done")
         print(json.dumps(line))

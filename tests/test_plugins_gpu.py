@@ -79,3 +79,45 @@ def test_gligen_plugin(cuda):
         r = _rel(outs[b]["latents"].cpu(), ref["latents"])
         print("gligen image", b, "final-latent rel-L2", r)
         assert r < 5e-2, r
+
+
+def test_backward_guidance_sd21_768_v_prediction(cuda):
+    """BASELINE config 3 geometry through the plug-in: SD2.1 shapes (heads 5/10/20/20 at head_dim 64, 1024-wide context,
+    Linear proj), 768x768 (96x96 latents: 144 / 576-token guidance maps), v-prediction, ratio-based energy; one image,
+    two denoising steps, one guidance iteration - against the fp32 oracle loop run live on the host cores"""
+    import os
+    from lgd_b200.env import SyntheticEnv
+    from lgd_b200.generation import backward_guidance as plug, common
+    from lgd_b200.unet import B200UNet, UNetConfig
+    from oracle import pipeline_ref, unet_ref
+    import lgd_b200.latents as L
+    torch.set_num_threads(min(os.cpu_count() or 1, 64))
+    ocfg = unet_ref.UNetConfig.sd21()
+    w = unet_ref.make_weights(ocfg, seed=4, qk_gain=1.0)
+    net = B200UNet(UNetConfig.sd21(), w, "cuda:0")
+    env = SyntheticEnv(ctx_dim=1024)
+    common.configure(net, env)
+    spec = dict(prompt="", gen_boxes=[("a cat", [90, 150, 300, 375]), ("a dog", [420, 300, 300, 330])],
+                bg_prompt="a photo of a park", extra_neg_prompt="")
+    steps = 2
+    outs = plug.run_batch([spec], [3], num_inference_steps=steps, height=768, width=768, prediction_type="v_prediction",
+                          overall_loss_scale=30, overall_loss_threshold=0.2, overall_max_iter=1, overall_max_index_step=1,
+                          return_latents=True)
+    torch.cuda.synchronize()
+    st = outs[0]["guidance_state"]
+    _, prompt, pwb = common.convert_spec(spec, 768, 768)
+    phrases, words, bboxes = [p for p, _, _ in pwb], [x for _, x, _ in pwb], [x for _, _, x in pwb]
+    pos, widx, prompt = env.phrase_indices(prompt, phrases, words)
+    unc, cnd = env.encode_prompts([prompt], common.DEFAULT_OVERALL_NEGATIVE_PROMPT)
+    g = pipeline_ref.GuidanceCfg([list(map(tuple, x)) for x in bboxes], pos, KEYS, 30, 0.2, 1, 1, use_ratio_based_loss=True)
+    tr = []
+    ref = pipeline_ref.denoise(w, ocfg, L.seeded_noise(3, 4, 96, 96), unc, cnd, steps, g=g, trace=tr,
+                               prediction_type="v_prediction")
+    ours_iters = [it[0] for it in st.iters]
+    first = st.trace[0][2][0]
+    r = _rel(outs[0]["latents"].cpu(), ref["latents"])
+    print("config-3 geometry: first loss ours", first, "oracle", tr[0][2], "iters", ours_iters, ref["iters"],
+          "final-latent rel-L2", r)
+    assert abs(first - tr[0][2]) < 1e-2 * abs(tr[0][2])
+    assert ours_iters == ref["iters"] == [1, 0]
+    assert r < 2e-2, r
