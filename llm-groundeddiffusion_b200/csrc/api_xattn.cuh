@@ -139,6 +139,27 @@ inline void launch_fused_t(const CUtensorMap& tmX, const CUtensorMap& tmWq, cons
                                     Cfg::SMEM_BYTES));
     done = true;
   }
+  // forward-progress guard for the cross-CTA spin-waits: the two clusters of a row tile (8 heads) and, with the loss on,
+  // every row tile of an image must be able to be resident together.  Queried once per device (first launch is eager).
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1024);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    B200_CHECK(cudaOccupancyMaxActiveClusters(&n, xattn_fused_kernel<D>, &cfg));
+    max_clusters = n;
+  }
+  const int need = p.has_loss ? 2 * p.tiles_per_img : 2;
+  if (need > max_clusters)
+    throw std::runtime_error("xattn_fused: the hand-shake needs " + std::to_string(need) + " co-resident clusters, the "
+                             "device can hold " + std::to_string(max_clusters) + " (MIG / MPS slice?) - use the unfused path");
   xattn_fused_kernel<D><<<dim3(row_tiles * 8), 192, Cfg::SMEM_BYTES, st>>>(tmX, tmWq, tmK, tmVt, tmO, tmWo, p);
   B200_CHECK(cudaGetLastError());
 }
