@@ -71,7 +71,7 @@ class Clocks(threading.Thread):
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -366,7 +366,7 @@ def main():
         host = lat.cpu()                                  # device -> host read of the step's result
         io["d2h"] = host.numel() * host.element_size()
         if outs[0].image is not None:                     # decoded pictures already crossed to the host in env.decode
-            io["d2h"] += sum(o.image.nbytes + sum(im.nbytes for im in o.so_img_list) for o in outs)
+            io["d2h"] += sum(o.image.nbytes + sum(im.nbytes for im in (o.so_img_list or [])) for o in outs)
         st = outs[0]["guidance_state"]
         if wl == "boxdiff":
             last["iters"] = [len(getattr(st, "boxdiff_losses", []))] * len(outs)
@@ -382,8 +382,11 @@ def main():
 
     def timed(env, k, fixed=True):
         barrier()
+        # only rank 0 samples clocks (its own GPU): eight ranks each forking nvidia-smi five times a second is host
+        # load that competes with the ranks' launch loops
         clk = Clocks(local)
-        clk.start()
+        if rank == 0:
+            clk.start()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

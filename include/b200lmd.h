@@ -94,6 +94,17 @@ int b200lmd_cfg_ddim_blend(void* z, const void* eps, int ld_eps, int B, int Cz, 
                            const void* mask, void* stream);
 int b200lmd_latent_update(void* z, const void* grad, int ld_g, int B, int Cz, int HW, float step_scale,
                           float inv_gscale, const int* active, void* stream);
+/* Per-image guidance-loop predicate on the device (models/pipelines.py:30: `while loss/loss_scale > loss_threshold and
+ * iteration < max_iter`, batched): `begin` resets the per-step counters and evaluates the predicate on the carried loss;
+ * `advance` (after the guidance launch sequence and latent_update) reduces the loss partials parts[n_keys][B*heads] in a
+ * fixed order, lets the images that were active take the new loss / count an iteration, records the trace row `slot`
+ * and re-evaluates the predicate.  active[B] feeds b200lmd_latent_update; any_active[1] is what the host reads (and
+ * only when the iteration count is data dependent).  loss / trace_loss are float64. */
+int b200lmd_guidance_loop_begin(void* loss_f64, int* it, int* active, const int* has_boxes, int* any_active, int B,
+                                double loss_scale, double threshold, int max_iter, void* stream);
+int b200lmd_guidance_loop_advance(void* loss_f64, int* it, int* active, const int* has_boxes, void* trace_loss_f64,
+                                  int* trace_active, int* any_active, const void* parts_f32, int n_keys, int B, int heads,
+                                  double loss_scale, double threshold, int max_iter, int slot, void* stream);
 /* Device-side latent composition between the two phases (utils/latents.py:37-118 compose_latents_with_alignment):
  * out[s,b,c,y,x] gathers from the per-box trajectory lat[s, owner-1, c, y-dy, x-dx] (zero outside) that owns the cell;
  * unowned cells are 0 for s > 0 and, for s = 0, the box-mask layer (bowner) over the background latent bg[B,C,H,W].

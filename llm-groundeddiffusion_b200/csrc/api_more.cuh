@@ -196,6 +196,85 @@ extern "C" int b200lmd_position_embed(const void* boxes, const void* masks, cons
 }
 
 namespace b200 {
+// Per-image guidance-loop state on the device (models/pipelines.py:16-82 batched over B images): after every guidance
+// iteration the loss partials the attention kernels wrote are reduced in a fixed order, the images that were active take
+// the new loss and count one more iteration, and the loop predicate `loss / loss_scale > threshold && it < max_iter` is
+// re-evaluated per image - so the host never uploads an active mask and reads back one small trace row, and only when
+// the iteration count is data dependent.  One block, one thread per image.
+struct GuidanceLoopState {
+  double* loss;          // [B] scaled loss carried across steps (the reference's `loss`, initialised to 10000 * ... on the host)
+  int* it;               // [B] iterations done in the current step
+  int* active;           // [B] 1 = this image runs the next iteration (read by latent_update_kernel)
+  const int* has_boxes;  // [B]
+  double* trace_loss;    // [cap][B] loss after each iteration of the current step
+  int* trace_active;     // [cap][B] which images took part in it
+  int* any_active;       // [1]
+};
+__global__ void guidance_loop_begin_kernel(GuidanceLoopState s, int B, double loss_scale, double threshold, int max_iter) {
+  __shared__ int any;
+  if (threadIdx.x == 0) any = 0;
+  __syncthreads();
+  const int b = threadIdx.x;
+  if (b < B) {
+    s.it[b] = 0;
+    const int a = s.has_boxes[b] && (s.loss[b] / loss_scale > threshold) && (0 < max_iter);
+    s.active[b] = a;
+    if (a) atomicOr(&any, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *s.any_active = any;
+}
+__global__ void guidance_loop_advance_kernel(GuidanceLoopState s, const float* __restrict__ parts, int n_keys, int B,
+                                             int heads, double loss_scale, double threshold, int max_iter, int slot) {
+  __shared__ int any;
+  if (threadIdx.x == 0) any = 0;
+  __syncthreads();
+  const int b = threadIdx.x;
+  if (b < B) {
+    const int was = s.active[b];
+    if (was) {
+      double acc = 0.0;                       // fixed order: key-major, then head
+      for (int k = 0; k < n_keys; ++k)
+        for (int h = 0; h < heads; ++h) acc += (double)parts[((long long)k * B + b) * heads + h];
+      s.loss[b] = acc;
+      s.it[b] += 1;
+    }
+    s.trace_loss[(long long)slot * B + b] = s.loss[b];
+    s.trace_active[(long long)slot * B + b] = was;
+    const int a = was && (s.loss[b] / loss_scale > threshold) && (s.it[b] < max_iter);
+    s.active[b] = a;
+    if (a) atomicOr(&any, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *s.any_active = any;
+}
+}  // namespace b200
+
+extern "C" int b200lmd_guidance_loop_begin(void* loss_f64, int* it, int* active, const int* has_boxes, int* any_active,
+                                           int B, double loss_scale, double threshold, int max_iter, void* stream) {
+  return b200::guarded([&] {
+    using namespace b200;
+    if (B > 1024) throw std::runtime_error("guidance loop state: at most 1024 images per batch");
+    GuidanceLoopState s{(double*)loss_f64, it, active, has_boxes, nullptr, nullptr, any_active};
+    guidance_loop_begin_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(s, B, loss_scale, threshold, max_iter);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+extern "C" int b200lmd_guidance_loop_advance(void* loss_f64, int* it, int* active, const int* has_boxes,
+                                             void* trace_loss_f64, int* trace_active, int* any_active, const void* parts_f32,
+                                             int n_keys, int B, int heads, double loss_scale, double threshold,
+                                             int max_iter, int slot, void* stream) {
+  return b200::guarded([&] {
+    using namespace b200;
+    if (B > 1024) throw std::runtime_error("guidance loop state: at most 1024 images per batch");
+    GuidanceLoopState s{(double*)loss_f64, it, active, has_boxes, (double*)trace_loss_f64, trace_active, any_active};
+    guidance_loop_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(
+        s, (const float*)parts_f32, n_keys, B, heads, loss_scale, threshold, max_iter, slot);
+    B200_CHECK(cudaGetLastError());
+  });
+}
+
+namespace b200 {
 // Device-side latent composition (utils/latents.py:37-83 compose_latents, after the per-box shifts of :85-118): every
 // output cell gathers from the per-box trajectory that owns it.
 //   lat     fp32 [S, BA, C, H, W]  all steps of the per-box generations (stays on the GPU after Phase A)

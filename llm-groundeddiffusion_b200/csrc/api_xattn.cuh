@@ -79,8 +79,11 @@ extern "C" int b200lmd_xattn_fwd_f16(const void* q, const void* k, const void* v
 extern "C" int b200lmd_max_loss_slots(void) { return b200::kMaxSlots; }
 
 namespace b200 {
+// A/B switch (b200lmd_set_option "fused_loss_stage"): staging the loss inputs in shared memory with one cooperative
+// pass measured no faster than per-problem loads (profiles/r2/xattn_fused_timeline_call3.txt: 9.2 vs 8.5 us for the
+// problem loop) - every L2 round trip of the epilogue warps queues behind phase 2's TMA stream either way - so it is off
 inline bool& fused_loss_stage() {
-  static bool on = true;
+  static bool on = false;
   return on;
 }
 inline unsigned long long*& fused_dbg() {

@@ -192,9 +192,28 @@ def guidance_step_scale(sched, index, t):
     return float((1.0 - sched.alphas_cumprod[int(t)]) ** 0.5)
 
 
+class _LoopState:
+    """device-resident per-image loop state of latent_backward_guidance (loss carried across steps, iteration counters,
+    active mask, trace rows of the current step) + a pinned host mirror for the one small read-back per iteration"""
+
+    def __init__(self, B, has_boxes, dev, cap=64):
+        self.B, self.cap = B, cap
+        self.loss = torch.full((B,), 10000.0, dtype=torch.float64, device=dev)
+        self.it = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.active = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.has_boxes = torch.from_numpy(has_boxes.astype(np.int32)).to(dev)
+        self.trace_loss = torch.zeros(cap, B, dtype=torch.float64, device=dev)
+        self.trace_active = torch.zeros(cap, B, dtype=torch.int32, device=dev)
+        self.any = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.any_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+
 def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spec: GuidanceSpec, state: GuidanceState,
                              objs=None, fuser_on=False, use_graphs=False):
-    """models/pipelines.py:16-82, batched with per-image predicates.  z: device fp32 [B,4,H,W], updated in place."""
+    """models/pipelines.py:16-82, batched with per-image predicates evaluated ON THE DEVICE
+    (b200lmd_guidance_loop_begin / _advance): no active mask is uploaded and the loss partials are not read back; per
+    iteration the host reads one int (does any image continue?), per step one trace block.
+    z: device fp32 [B,4,H,W], updated in place."""
     B, Cz, H, W = z.shape
     it = np.zeros(B, dtype=np.int64)
     if index >= spec.max_index_step or all(len(l.bboxes) == 0 for l in spec.layouts):
@@ -203,8 +222,18 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
     mi = spec.max_iter
     if isinstance(mi, list):
         mi = mi[index] if len(mi) > index else mi[-1]
+    mi = int(mi)
     has_boxes = np.array([len(l.bboxes) > 0 for l in spec.layouts])
-    active = has_boxes & (state.loss / spec.loss_scale > spec.loss_threshold) & (it < mi)
+    # the host mirrors the carried loss (refreshed from the trace block at the end of every guided step), so whether the
+    # loop is entered at all needs no device round trip
+    if not (has_boxes & (state.loss / spec.loss_scale > spec.loss_threshold) & (0 < mi)).any():
+        state.iters.append(it.tolist())
+        return
+    ls = state.__dict__.get("loop")
+    if ls is None:
+        ls = state.loop = _LoopState(B, has_boxes, z.device)
+    if mi > ls.cap:
+        raise ValueError(f"max_iter {mi} exceeds the trace capacity {ls.cap}")
     losses = state.losses
     if losses is not None:
         for kl in losses.values():
@@ -214,7 +243,12 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
     t_dev = state.t_dev
     t_dev.fill_(float(t))
     step_scale = guidance_step_scale(sched, index, t)
-    while active.any():
+    S = cur_stream()
+    _d = ctypes.c_double
+    check(lib().b200lmd_guidance_loop_begin(ptr(ls.loss), ptr(ls.it), ptr(ls.active), ptr(ls.has_boxes), ptr(ls.any),
+                                            _i(B), _d(spec.loss_scale), _d(spec.loss_threshold), _i(mi), S))
+    n_done, go = 0, True
+    while go and n_done < mi:
         if losses is None:
             ctx = state.ctx
             reuse = (ctx.losses, ctx.slot_dev) if (ctx is not None and ctx.losses is not None) else None
@@ -233,14 +267,24 @@ def latent_backward_guidance(net, sched: DDIMSchedule, z, t, index, kv_cond, spe
             grad, parts = state.graphs[fuser_on]()
         else:
             grad, parts = net.guidance_gradient_launch(z, t_dev, kv_cond, losses, objs=objs, fuser_on=fuser_on)
-        loss_new = net.reduce_loss(parts, B)
-        act_dev = torch.from_numpy(active.astype(np.int32)).to(z.device)
         check(lib().b200lmd_latent_update(ptr(z), ptr(grad), _i(grad.shape[2]), _i(B), _i(Cz), _i(H * W),
-                                          _f(step_scale), _f(1.0 / net.gscale), ptr(act_dev), cur_stream()))
-        state.loss[active] = loss_new[active]
-        it[active] += 1
-        state.trace.append((index, int(it.max()), state.loss.copy().tolist(), active.tolist()))
-        active = active & (state.loss / spec.loss_scale > spec.loss_threshold) & (it < mi)
+                                          _f(step_scale), _f(1.0 / net.gscale), ptr(ls.active), S))
+        check(lib().b200lmd_guidance_loop_advance(
+            ptr(ls.loss), ptr(ls.it), ptr(ls.active), ptr(ls.has_boxes), ptr(ls.trace_loss), ptr(ls.trace_active),
+            ptr(ls.any), ptr(parts), _i(parts.shape[0]), _i(B), _i(parts.shape[1] // B), _d(spec.loss_scale),
+            _d(spec.loss_threshold), _i(mi), _i(n_done), S))
+        n_done += 1
+        if n_done < mi:                         # does any image continue? (one int; the reference reads loss.item())
+            ls.any_host.copy_(ls.any, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            go = bool(ls.any_host[0])
+    # one read-back per guided step: the trace rows of this step
+    tl = ls.trace_loss[:n_done].cpu().numpy()
+    ta = ls.trace_active[:n_done].cpu().numpy().astype(bool)
+    for j in range(n_done):
+        it[ta[j]] += 1
+        state.loss = np.where(ta[j], tl[j], state.loss)
+        state.trace.append((index, j + 1, tl[j].tolist(), ta[j].tolist()))
     state.iters.append(it.tolist())
 
 
