@@ -118,23 +118,45 @@ class BoxDiffLoss:
                              "(torch.cat over keys, utils/boxdiff.py:146)")
         self.n, self.heads = ns.pop(), hs.pop()
         self.side = int(round(self.n ** 0.5))
-        for lay in spec.layouts:
-            for pos in lay.object_positions:
-                for tok in pos:
-                    if not 1 <= tok <= T - 2:
-                        raise ValueError(f"BoxDiff: token index {tok} outside 1..{T - 2} (first and last token are dropped)")
-        off, terms, masks, corner = build_tables(spec.layouts, self.side, spec.P, spec.L)
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
-        self.term_off = torch.from_numpy(off).to(dev)
-        self.terms = up(terms) if len(terms) else torch.zeros(TERM_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-        self.masks, self.corner = torch.from_numpy(masks).to(dev), torch.from_numpy(corner).to(dev)
+        # fixed-capacity device tables refilled in place by update(): their addresses live in captured CUDA graphs
+        self.cap_terms, self.cap_masks = self.B * 64, self.B * 16
+        self.term_off = torch.zeros(self.B + 1, dtype=torch.int32, device=dev)
+        self.terms = torch.zeros(self.cap_terms * TERM_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.masks = torch.zeros(self.cap_masks, self.n, dtype=torch.uint8, device=dev)
+        self.corner = torch.zeros(self.cap_masks, 2 * self.side, dtype=torch.uint8, device=dev)
         self.holders = {k: _Holder(self.B * self.heads, self.n, dev, ext_ld) for k in spec.keys}
         self.mean = torch.empty(self.B, self.n, T, device=dev, dtype=torch.float32)
         self.dA = torch.empty(self.B, self.n, T, device=dev, dtype=torch.float32)
         self.loss = torch.zeros(self.B, device=dev, dtype=torch.float32)
-        self.kern = gaussian_kernel(spec.kernel_size, spec.sigma)
         if spec.smooth_attentions and spec.kernel_size != 3:
             raise NotImplementedError("BoxDiff smoothing: 3x3 kernel only (the reference's default)")
+        if not self.update(spec):
+            raise ValueError("BoxDiff: more than 64 phrase tokens or 16 phrases per image")
+
+    def update(self, spec: BoxDiffSpec):
+        """refill the tables for a new batch of layouts of the same shape; False when they do not fit the capacity or
+        the structure (batch size, keys, smoothing) differs - the caller then builds a fresh object and re-captures"""
+        if len(spec.layouts) != self.B or list(spec.keys) != list(self.spec.keys) or \
+                (spec.smooth_attentions, spec.kernel_size, spec.sigma) != \
+                (self.spec.smooth_attentions, self.spec.kernel_size, self.spec.sigma):      # travel by value in the launch
+            return False
+        for lay in spec.layouts:
+            for pos in lay.object_positions:
+                for tok in pos:
+                    if not 1 <= tok <= self.T - 2:
+                        raise ValueError(f"BoxDiff: token index {tok} outside 1..{self.T - 2} (first and last token are dropped)")
+        off, terms, masks, corner = build_tables(spec.layouts, self.side, spec.P, spec.L)
+        if len(terms) > self.cap_terms or len(masks) > self.cap_masks:
+            return False
+        self.spec = spec
+        self.term_off.copy_(torch.from_numpy(off))
+        if len(terms):
+            raw = torch.from_numpy(np.ascontiguousarray(terms).view(np.uint8).reshape(-1).copy())
+            self.terms[:raw.numel()].copy_(raw)
+        self.masks[:masks.shape[0]].copy_(torch.from_numpy(masks))
+        self.corner[:corner.shape[0]].copy_(torch.from_numpy(corner))
+        self.kern = gaussian_kernel(spec.kernel_size, spec.sigma)
+        return True
 
     def launch(self, saved):
         """saved: the dict B200UNet filled during guidance_forward: key -> {"probs": fp16 [B, heads, n, T]}"""

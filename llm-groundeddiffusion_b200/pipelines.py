@@ -111,10 +111,19 @@ class CudaGraph:
             if warmed is not None and key is not None:
                 warmed.add(key)
         self.graph = torch.cuda.CUDAGraph()
-        # one memory pool per owner for all of its graphs: a capture then reuses the blocks earlier captures left in the
-        # pool instead of cudaMalloc-ing every intermediate again (the graphs replay on one stream, never concurrently,
-        # and their outputs stay referenced, so sharing is safe)
-        pool = owner.__dict__.setdefault("_graph_pool", torch.cuda.graph_pool_handle()) if owner is not None else None
+        # one memory pool per owner for all of its live graphs: a capture then reuses the blocks earlier captures left in
+        # the pool instead of cudaMalloc-ing every intermediate again (the graphs replay on one stream, never
+        # concurrently, and their outputs stay referenced, so sharing is safe).  A pool handle is only valid while at
+        # least one graph captured into it is alive, so the owner tracks its live graphs and takes a fresh handle when
+        # the last one has gone.
+        pool = None
+        if owner is not None:
+            import weakref
+            rec = owner.__dict__.get("_graph_pool")
+            if rec is None or len(rec[1]) == 0:
+                rec = owner.__dict__["_graph_pool"] = (torch.cuda.graph_pool_handle(), weakref.WeakSet())
+            pool = rec[0]
+            rec[1].add(self)
         with torch.cuda.graph(self.graph, pool=pool):
             self.out = fn()
         CudaGraph.capture_seconds += time.perf_counter() - t0
@@ -296,8 +305,8 @@ class DenoiseCtx:
 
     def __init__(self):
         self.z = self.t2 = self.tok_dev = self.kv = self.objs_main = None
-        self.fwd_graphs, self.guid_graphs = {}, {}
-        self.losses = self.slot_dev = None
+        self.fwd_graphs, self.guid_graphs, self.bd_graphs = {}, {}, {}
+        self.losses = self.slot_dev = self.bd = self.t_dev = None
 
 
 def _denoise_ctx(net, key):
@@ -330,10 +339,11 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
         t_start, cap0 = time.perf_counter(), CudaGraph.capture_seconds
     B, Cz, H, W = z0.shape
     ctx = None
-    if use_graphs and boxdiff is None:
+    if use_graphs:
         key = (B, Cz, H, W, tuple(uncond.shape[1:]), tuple(cond.shape[1:]), gligen is not None,
                tuple(save_keys) if save_keys is not None else None, save_tok is not None,
-               tuple(guidance.keys) if guidance is not None else None, prediction_type)
+               tuple(guidance.keys) if guidance is not None else None, prediction_type,
+               ("boxdiff",) + tuple(boxdiff.keys) if boxdiff is not None else None)
         ctx = _denoise_ctx(net, key)
     if ctx is not None and ctx.z is not None:
         z = ctx.z
@@ -402,15 +412,22 @@ def denoise(net, z0, uncond, cond, steps, guidance_scale=7.5, guidance: Optional
         torch.cuda.synchronize()
         t_loop = time.perf_counter()
     bd = bd_active = None
-    bd_graphs = {}
+    bd_graphs = ctx.bd_graphs if ctx is not None else {}
     for index, t in enumerate(sched.timesteps):
         fuser_on = gligen is not None and index < n_ground
         if boxdiff is not None and index < boxdiff.max_index_step and any(len(l.bboxes) for l in boxdiff.layouts):
             from . import boxdiff as BD
             if bd is None:
-                bd = BD.BoxDiffLoss(net, boxdiff, H, W, kv.T)
+                if ctx is not None and ctx.bd is not None and ctx.bd.update(boxdiff):
+                    bd = ctx.bd                          # tables refilled in place: the captured graphs stay valid
+                else:
+                    bd = BD.BoxDiffLoss(net, boxdiff, H, W, kv.T)
+                    bd_graphs.clear()
+                    if ctx is not None:
+                        ctx.bd = bd
                 bd_active = torch.tensor([int(len(l.bboxes) > 0) for l in boxdiff.layouts], dtype=torch.int32, device=dev)
-                state.t_dev = torch.empty(B, device=dev, dtype=torch.float32)
+                if state.t_dev is None:
+                    state.t_dev = torch.empty(B, device=dev, dtype=torch.float32)
                 state.boxdiff_losses = []
             state.t_dev.fill_(float(t))
             if use_graphs:
