@@ -415,9 +415,10 @@ def main():
     iters_b = list(last["iters"])
     log(f"timed (resident inputs, fixed 65 iterations): {ms:.1f} ms for {args.steps} step(s)")
     env_host.bytes_out = 0
-    ms_e2e, _, _ = timed(env_host, args.steps)
-    log(f"timed (host inputs, e2e): {ms_e2e:.1f} ms")
-    io["h2d"] = env_host.bytes_out // max(1, args.steps)
+    k_e2e = min(args.steps, 8)             # bounded: the end-to-end leg repeats the same step with host inputs
+    ms_e2e, _, _ = timed(env_host, k_e2e)
+    log(f"timed (host inputs, e2e): {ms_e2e:.1f} ms for {k_e2e} step(s)")
+    io["h2d"] = env_host.bytes_out // max(1, k_e2e)
     imgs = args.batch * world * args.steps
     metric = {"lmd_plus": "images/sec (LMD+ SD1.5, 50 steps, 512^2)",
               "backward_guidance_sd21": "images/sec (backward guidance SD2.1 shapes, 50 steps, 768^2)",
@@ -427,8 +428,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": config, "clocks": clocks, "gpu_launches": launches,
             "guidance_iterations_per_image": iters_b, "host_threads": pin,
-            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": io["h2d"],
-                    "d2h_bytes_per_step": io["d2h"]}}
+            "e2e": {"value": args.batch * world * k_e2e / (ms_e2e * 1e-3), "unit": "images/s", "steps": k_e2e,
+                    "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"]}}
     if not args.no_mode_a and wl == "lmd_plus":
         step(env_res, fixed=False)                  # graphs / tables of the data-dependent variant
         ms_a, _, _ = timed(env_res, 1, fixed=False)
