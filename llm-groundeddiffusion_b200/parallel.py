@@ -55,12 +55,17 @@ def _parse_cpu_list(s):
 
 def gpu_cpu_affinity():
     """{gpu index: [cpu ids]} from `nvidia-smi topo -m` (the 'CPU Affinity' column); {} when unavailable"""
-    import re
     import subprocess
     try:
         txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
     except Exception:
         return {}
+    return parse_topo(txt)
+
+
+def parse_topo(txt):
+    """the GPU rows of `nvidia-smi topo -m`: first token that is a CPU list (digits, '-' and ',') after the link columns"""
+    import re
     aff = {}
     for line in txt.splitlines():
         m = re.match(r"^GPU(\d+)\s", line)

@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE.  Usage (from the repo root):
     python -m oracle.make_goldens_layout config1        # BASELINE config 1: LMD, SD1.5 widths, fp32 CPU, 10 steps,
                                                         # 2 boxes, bg_seed 0, fg_seed_start 20  (~1 h on 8 cores)
     python -m oracle.make_goldens_layout lmdplus_tiny   # LMD+ (GLIGEN) at the small topology, 2 specs, 6 steps
+    python -m oracle.make_goldens_layout lmdplus_sd15   # LMD+ at SD1.5+GLIGEN widths, 2 boxes, 10 steps (~45 min)
     python -m oracle.make_goldens_layout lmd_tiny       # LMD at the small topology (fast-schedule variant)
 
 Stated deviations from a stock run: synthetic seeded weights / text embeddings (no checkpoints
@@ -44,12 +45,14 @@ CASES = {
                       max_iter=[2, 1], overall_max_iter=[2, 1]), 4),
     "lmdplus_tiny": ("lmd_plus", "tiny_gligen", 0, [(DEER_BEAR, 0, 20), (TWO_CATS, 7, 30)],
                      dict(num_inference_steps=6, overall_max_iter=[2, 2, 1], overall_max_index_step=4), None),
+    # the benchmarked function at the benchmark's widths: LMD+ (SD1.4/1.5 + GLIGEN shapes), 2 boxes, 10 steps
+    "lmdplus_sd15": ("lmd_plus", "sd15_gligen", 0, [(DEER_BEAR, 0, 20)], dict(num_inference_steps=10), None),
 }
 
 
 def config_of(name):
-    return {"sd15": unet_ref.UNetConfig.sd15(), "tiny": unet_ref.UNetConfig.tiny(),
-            "tiny_gligen": unet_ref.UNetConfig.tiny(gligen=True)}[name]
+    return {"sd15": unet_ref.UNetConfig.sd15(), "sd15_gligen": unet_ref.UNetConfig.sd15(gligen=True),
+            "tiny": unet_ref.UNetConfig.tiny(), "tiny_gligen": unet_ref.UNetConfig.tiny(gligen=True)}[name]
 
 
 def mint(name):

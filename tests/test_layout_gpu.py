@@ -8,6 +8,7 @@ weights, same offline tokenizer / text-encoder / VAE stand-ins of oracle/fakes.p
                        10 steps, bg_seed 0, fg_seed_start 20 - the stated parity configuration
   layout_lmd_tiny      LMD at the small topology with the fast schedule
   layout_lmdplus_tiny  LMD+ (GLIGEN, reference-attention transfer, frozen blend), 2 specs in one batch
+  layout_lmdplus_sd15  LMD+ at SD1.5+GLIGEN widths (the shapes bench.py times), 2 boxes, 10 steps
 
 Integer artefacts (guidance iteration counts per step, masks) must match exactly; the first loss of every generation
 starts from identical inputs (tight); final latents carry the fp16-activation vs fp32 difference through the whole
@@ -47,9 +48,10 @@ def _run_ours(name):
         pytest.skip(f"{path} not minted")
     g = np.load(path, allow_pickle=False)
     meta = json.loads(str(g["meta"]))
-    ocfg = {"sd15": unet_ref.UNetConfig.sd15(), "tiny": unet_ref.UNetConfig.tiny(),
-            "tiny_gligen": unet_ref.UNetConfig.tiny(gligen=True)}[meta["cfg"]]
-    cfg = {"sd15": UNetConfig.sd15(), "tiny": UNetConfig.tiny(), "tiny_gligen": UNetConfig.tiny(gligen=True)}[meta["cfg"]]
+    ocfg = {"sd15": unet_ref.UNetConfig.sd15(), "sd15_gligen": unet_ref.UNetConfig.sd15(gligen=True),
+            "tiny": unet_ref.UNetConfig.tiny(), "tiny_gligen": unet_ref.UNetConfig.tiny(gligen=True)}[meta["cfg"]]
+    cfg = {"sd15": UNetConfig.sd15(), "sd15_gligen": UNetConfig.sd15(gligen=True), "tiny": UNetConfig.tiny(),
+           "tiny_gligen": UNetConfig.tiny(gligen=True)}[meta["cfg"]]
     w = unet_ref.make_weights(ocfg, seed=meta["weight_seed"])
     net = B200UNet(cfg, w, "cuda:0")
     del w
@@ -162,6 +164,12 @@ def test_lmd_run_config1_sd15_vs_reference(cuda):
     # measured (profiles/r2/layout_parity_config1.json): iteration counts exact (35 per generation), per-box final latents
     # 5.1e-3 / 5.5e-3, overall final latents 1.55e-2 after 105 guidance iterations, loss traces within 1.3e-3
     _check("config1", tol_final=0.035, tol_so=0.012)
+
+
+def test_lmd_plus_run_sd15_gligen_vs_reference(cuda):
+    """the benchmarked function (`lmd_plus.run_batch` -> layout_generation) at the benchmark's widths (SD1.4/1.5 + GLIGEN
+    shapes, fusers, reference-attention transfer, frozen blend) vs the UNMODIFIED generation/lmd_plus.py"""
+    _check("lmdplus_sd15", tol_final=0.04, tol_so=0.015)
 
 
 def test_device_composition_matches_host_mirror(cuda):

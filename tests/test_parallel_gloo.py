@@ -44,3 +44,16 @@ def test_two_rank_broadcast_and_sharding():
     assert res[0][1] == res[1][1]                       # identical weights on both ranks
     assert res[0][2] == list(range(8)) and res[1][2] == list(range(8, 16))
     assert res[0][3] == res[1][3] == 11.0
+
+
+def test_topo_parsing_and_rank_slices():
+    """NUMA pinning input: the 'CPU Affinity' column of `nvidia-smi topo -m` (sample from the B200 box)"""
+    import lgd_b200  # noqa: F401
+    from lgd_b200 import parallel
+    txt = "\n".join(["\tGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID",
+                     "GPU0\t X \tNV18\tSYS\t32-63,96-127\t1\t\tN/A",
+                     "GPU1\tNV18\t X \tNODE\t0-31,64-95\t0\t\tN/A",
+                     "NIC0\tSYS\tNODE\t X \t\t\t"])
+    aff = parallel.parse_topo(txt)
+    assert aff[0][:3] == [32, 33, 34] and len(aff[0]) == 64 and aff[1][-1] == 95
+    assert parallel._parse_cpu_list("0-3,8") == [0, 1, 2, 3, 8]
