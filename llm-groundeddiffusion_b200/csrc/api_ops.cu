@@ -261,8 +261,18 @@ extern "C" int b200lmd_groupnorm_bwd_f16(const void* dy, const void* x, const vo
 extern "C" int b200lmd_layernorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* stats,
                                      long long rows, int C, float eps, void* stream) {
   return guarded([&] {
-    ln_fwd_kernel<<<ew_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, (const float*)gamma, (const float*)beta, (__half*)y, (float*)stats, rows, C, eps);
+    if (C % 8) throw std::runtime_error("LayerNorm: C must be a multiple of 8");
+    const int vecs = C >> 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vecs <= 64)
+      ln_fwd_rows_kernel<2, 4, 2><<<ew_grid((rows + 3) / 4 * 32, 256), 256, 0, st>>>(
+          (const __half*)x, (const float*)gamma, (const float*)beta, (__half*)y, (float*)stats, rows, C, eps);
+    else if (vecs <= 96)
+      ln_fwd_rows_kernel<3, 2, 2><<<ew_grid((rows + 1) / 2 * 32, 256), 256, 0, st>>>(
+          (const __half*)x, (const float*)gamma, (const float*)beta, (__half*)y, (float*)stats, rows, C, eps);
+    else
+      ln_fwd_kernel<<<ew_grid(rows * 32, 256), 256, 0, st>>>(
+          (const __half*)x, (const float*)gamma, (const float*)beta, (__half*)y, (float*)stats, rows, C, eps);
     B200_CHECK(cudaGetLastError());
   });
 }

@@ -342,6 +342,74 @@ __global__ void ln_fwd_kernel(const __half* __restrict__ x, const float* __restr
   }
 }
 
+// LayerNorm forward for narrow rows (C <= 768): one warp works on RPW rows at a time, so VPL * RPW 16-byte loads per
+// lane are in flight instead of one or two (the one-row-per-warp kernel keeps ~15 KB per SM in flight at C = 320 and
+// ran at 0.38 of the HBM rate, profiles/r2/norm_kernels_ncu.md).  Same arithmetic and statistics layout.
+template <int VPL, int RPW, int MINB>
+__global__ void __launch_bounds__(256, MINB) ln_fwd_rows_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, __half* __restrict__ y, float* __restrict__ stats,
+                                   long long rows, int C, float eps) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int vecs = C >> 3;
+  const float inv_c = 1.f / (float)C;
+  for (long long row0 = (blockIdx.x * (long long)warps + (threadIdx.x >> 5)) * RPW; row0 < rows;
+       row0 += (long long)gridDim.x * warps * RPW) {
+    uint4 buf[RPW][VPL];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        buf[r][k] = (v < vecs && row0 + r < rows) ? *reinterpret_cast<const uint4*>(x + (row0 + r) * C + v * 8)
+                                                  : make_uint4(0, 0, 0, 0);
+      }
+    float mean[RPW], rstd[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        float f[8];
+        unpack8(buf[r][k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s += f[j];
+          q += f[j] * f[j];
+        }
+      }
+      s = warp_sum(s);
+      q = warp_sum(q);
+      mean[r] = s * inv_c;
+      rstd[r] = rsqrtf(fmaxf(q * inv_c - mean[r] * mean[r], 0.f) + eps);
+      if (stats && lane == 0 && row0 + r < rows) {
+        stats[(row0 + r) * 2] = mean[r];
+        stats[(row0 + r) * 2 + 1] = rstd[r];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = lane + 32 * k;
+      if (v < vecs) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          if (row0 + r < rows) {
+            float f[8];
+            unpack8(buf[r][k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean[r]) * rstd[r] * gg[j] + bb[j];
+            *reinterpret_cast<uint4*>(y + (row0 + r) * C + v * 8) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void ln_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ x,
                               const float* __restrict__ stats, const float* __restrict__ gamma,
                               __half* __restrict__ dx, long long rows, int C, int accumulate) {
