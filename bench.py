@@ -4,9 +4,10 @@ of the cross-attention+loss op and the reference's CPU path timed on the host co
 
 One "step" = one full batch of 8 images (Phase A: 32 per-box generations x 50 CFG steps with GLIGEN fusers for the first
 40 %; composition; Phase B: 8 overall generations x 50 CFG steps + attention-guidance forward/backward iterations for
-index < 30 + reference-attention transfer).  Synthetic data: seeded random weights with the real layer shapes, seeded
-text embeddings, seeded layouts (no checkpoints, vocabularies or datasets exist offline).  VAE / CLIP / SAM are outside
-the measured path (out of scope / "next"); the SAM mask is the box raster.  The headline `value` is
+index < 30 + reference-attention transfer; every generation ends in the B200 VAE decode, `--vae 0` leaves it out).
+Synthetic data: seeded random weights with the real layer shapes, seeded text embeddings, seeded layouts (no checkpoints,
+vocabularies or datasets exist offline).  CLIP / SAM are outside the measured path (out of scope /
+"next"); the SAM mask is the box raster.  The headline `value` is
 the fixed-iteration mode (B) of SURVEY.md section 8d - overall_loss_threshold=0, so every image runs all 65 guidance
 iterations and the FLOPs behind the number are known; mode (A), the reference's data-dependent thresholds, is timed
 beside it (`mode_a`) with its per-image iteration counts.

@@ -194,7 +194,10 @@ class B200UNet:
         return self.grads.get(t.data_ptr())
 
     def _acc(self, t, like=None):
-        """gradient buffer of tensor t and whether it already holds a value (=> accumulate)"""
+        """gradient buffer of tensor t and whether it already holds a value (=> accumulate).  Keyed by the data pointer on
+        purpose: the conv view [B,H,W,C] and the token view [B*n,C] of one activation are different tensor objects over
+        the same memory and must share one gradient; `_keep` pins every keyed tensor for the life of the tape, so a
+        pointer cannot be recycled under a live key."""
         g = self.grads.get(t.data_ptr())
         if g is not None:
             return g, True
