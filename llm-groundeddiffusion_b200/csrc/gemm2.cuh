@@ -26,7 +26,10 @@ struct Gemm2Cfg {
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
-template <int BLOCK_N>
+// MODE is the epilogue (EPI_ROWMAJOR / EPI_GEGLU / EPI_HEADS) as a template parameter: each variant gets its own
+// register allocation and instruction schedule (as one kernel with run-time mode tests, a change to the row-major
+// epilogue moved the GEGLU variant by 10-15 %, profiles/r2/ops_profile*.txt)
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(320, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmParams p, int m_tiles, int n_tiles) {
@@ -167,7 +170,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       };
       // EPI_HEADS: (image, token) of the rows this thread touches, once per tile (32-bit: M < 2^31)
       int pim[4] = {0, 0, 0, 0}, ptok[4] = {0, 0, 0, 0}, tok_me = 0;
-      if (p.mode == EPI_HEADS) {
+      if (MODE == EPI_HEADS) {
         const unsigned rpi = (unsigned)p.rows_per_img;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
@@ -179,7 +182,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       // residual / accumulate operand: fetched one chunk ahead into registers so its latency hides behind the
       // accumulator wait and the previous chunk's arithmetic
-      const bool rd = (p.mode == EPI_ROWMAJOR) && ((p.residual != nullptr) || p.accumulate_out);
+      const bool rd = (MODE == EPI_ROWMAJOR) && ((p.residual != nullptr) || p.accumulate_out);
       const __half* rsrc = p.residual ? p.residual : p.out;
       const int rlds = p.residual ? p.ldr : p.ldo;
       uint4 pre[4];
@@ -196,7 +199,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + ab * BLOCK_N + lane_off;
 
-      if (p.mode == EPI_GEGLU) {
+      if (MODE == EPI_GEGLU) {
         if constexpr (BLOCK_N == 128) {
           // 64 outputs per tile: value columns [0,64), gate columns [64,128); this thread: 32 of them
           uint32_t vv[32], gg[32];
@@ -307,7 +310,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             sts128(my_s + g * 16,
                    make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])));
           }
-          if (p.mode == EPI_HEADS) {
+          if (MODE == EPI_HEADS) {
             // transposed slabs: this thread's row is one token, lanes of a warp are consecutive tokens -> coalesced.
             // (projection, head, column-in-head) of the first 8-column group, then stepped without divisions
             if (row_ok) {
@@ -335,7 +338,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (p.mode == EPI_ROWMAJOR) {
+          if (MODE == EPI_ROWMAJOR) {
             const bool vec_ok = (p.ldo % 8 == 0);
             for_pieces([&](int row, int pc, long long orw) {
               const int n = nb + pc * 8;

@@ -164,19 +164,31 @@ inline bool& gemm_use_v2() {
   return v;
 }
 
-template <int BN>
-inline void launch_gemm2(const GemmLaunch& L, cudaStream_t st) {
+template <int BN, int MODE>
+inline void launch_gemm2_mode(const GemmLaunch& L, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    B200_CHECK(cudaFuncSetAttribute(gemm2_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CHECK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Gemm2Cfg<BN>::SMEM_BYTES));
     done = true;
   }
   const int m_tiles = (int)L.grid.y, n_tiles = (int)L.grid.x;
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = (int)(total < 148 ? total : 148);
-  gemm2_tc_kernel<BN><<<grid, 320, Gemm2Cfg<BN>::SMEM_BYTES, st>>>(L.tmA, L.tmB, L.p, m_tiles, n_tiles);
+  gemm2_tc_kernel<BN, MODE><<<grid, 320, Gemm2Cfg<BN>::SMEM_BYTES, st>>>(L.tmA, L.tmB, L.p, m_tiles, n_tiles);
   B200_CHECK(cudaGetLastError());
+}
+template <int BN>
+inline void launch_gemm2(const GemmLaunch& L, cudaStream_t st) {
+  switch (L.p.mode) {
+    case EPI_ROWMAJOR: launch_gemm2_mode<BN, EPI_ROWMAJOR>(L, st); break;
+    case EPI_GEGLU:
+      if (BN != 128) throw std::runtime_error("gemm2: the GEGLU epilogue needs 128-wide tiles");
+      launch_gemm2_mode<128, EPI_GEGLU>(L, st);
+      break;
+    case EPI_HEADS: launch_gemm2_mode<BN, EPI_HEADS>(L, st); break;
+    default: throw std::runtime_error("gemm2: unknown epilogue mode");
+  }
 }
 
 inline bool& gemm_use_v3() {
