@@ -169,7 +169,9 @@ def test_lmd_run_config1_sd15_vs_reference(cuda):
 def test_lmd_plus_run_sd15_gligen_vs_reference(cuda):
     """the benchmarked function (`lmd_plus.run_batch` -> layout_generation) at the benchmark's widths (SD1.4/1.5 + GLIGEN
     shapes, fusers, reference-attention transfer, frozen blend) vs the UNMODIFIED generation/lmd_plus.py"""
-    _check("lmdplus_sd15", tol_final=0.04, tol_so=0.015)
+    # measured (profiles/r2/layout_parity_lmdplus_sd15.json): iteration counts exact (35), per-box final latents 4.1e-3 /
+    # 4.2e-3, overall 4.6e-3, loss trace within 2.7e-4
+    _check("lmdplus_sd15", tol_final=0.01, tol_so=0.01)
 
 
 def test_device_composition_matches_host_mirror(cuda):
