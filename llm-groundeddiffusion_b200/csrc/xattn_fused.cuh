@@ -399,6 +399,16 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (++spins > B200_SPIN_LIMIT) __trap();
         __nanosleep(64);
       }
+      // the loss reduction needs the P columns of every row tile of this (image, head): wait for them HERE, inside the
+      // hand-shake this thread is already spinning in, instead of paying another L2 round trip after the cluster barrier
+      // (every tile publishes before it waits, so there is no circular wait)
+      if (p.has_loss) {
+        spins = 0;
+        while (atomicAdd(&p.bh_ready[bh], 0) < p.tiles_per_img) {
+          if (++spins > B200_SPIN_LIMIT) __trap();
+          __nanosleep(64);
+        }
+      }
       __threadfence();
       // every flag is back to zero when the kernel ends (no memset between launches): the last head to get here resets
       if (atomicAdd(&p.tile_done[rt], 1) == 7) {
@@ -469,15 +479,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // ---- guidance loss, overlapped with phase 2 on the tensor core: the row tiles of this (image, head) share the
     // problems once every tile's P columns are published (fenced before bh_ready went up)
     if (p.has_loss) {
-      if (tid == 0) {
-        uint32_t spins = 0;
-        while (atomicAdd(&p.bh_ready[bh], 0) < p.tiles_per_img) {
-          if (++spins > B200_SPIN_LIMIT) __trap();
-          __nanosleep(64);
-        }
-        __threadfence();
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // every tile's P columns are published: thread 0 saw bh_ready complete (and fenced) before the cluster barrier
       // staging area: the K/V region behind the residual / output staging rows (dead since the core)
       uint8_t* lstage = sK + 128 * OLD * 2;
       const int lstage_bytes = Cfg::K_BYTES + Cfg::V_BYTES - 128 * OLD * 2;
