@@ -466,6 +466,11 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     __half* stgE = reinterpret_cast<__half*>(sK);
     const uint32_t stgE_s = smem_u32(stgE);
     static_assert(128 * (D + 8) * 2 <= Cfg::K_BYTES + Cfg::V_BYTES, "residual staging must fit in the K/V region");
+    // output-projection bias of this head -> shared memory now (while phase 2 runs), so the epilogue loop below does not
+    // pay a global-load round trip per 16-column step
+    float* s_bias = reinterpret_cast<float*>(sK + Cfg::K_BYTES + Cfg::V_BYTES - 1024);
+    static_assert(128 * (D + 8) * 2 + 1024 <= Cfg::K_BYTES + Cfg::V_BYTES && D * 4 <= 1024, "bias staging must fit");
+    for (int i = tid; i < D; i += 128) s_bias[i] = p.bias_o ? __ldg(p.bias_o + h * D + i) : 0.f;
     if (p.residual) {
       // asynchronous copies (LDGSTS): nothing waits on them until the accumulator is needed
       for (int pi = tid; pi < 128 * PPR; pi += 128) {
@@ -482,15 +487,13 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       // every tile's P columns are published: thread 0 saw bh_ready complete (and fenced) before the cluster barrier
       // staging area: the K/V region behind the residual / output staging rows (dead since the core)
       uint8_t* lstage = sK + 128 * OLD * 2;
-      const int lstage_bytes = Cfg::K_BYTES + Cfg::V_BYTES - 128 * OLD * 2;
+      const int lstage_bytes = Cfg::K_BYTES + Cfg::V_BYTES - 128 * OLD * 2 - 1024;   // the last KB holds the bias
       loss_run(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, p.loss_partials, p.bh_done,
                p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr, p.bh_ready,
                fused_loss_stage_enabled(p) ? lstage : nullptr, lstage_bytes);
     }
-    if (p.residual) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
+    if (p.residual) asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // residual tile and bias are in shared memory
     mbar_wait(acc_full, 1);   // fourth completion
     tc_fence_after();
     FUSED_STAMP(6);
@@ -501,7 +504,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_ld_wait();
       float f[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + (p.bias_o ? __ldg(p.bias_o + h * D + c0 + i) : 0.f);
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + s_bias[c0 + i];
       if (p.residual) {
         const uint4 r0 = lds128(stgE_s + (r * OLD + c0) * 2), r1 = lds128(stgE_s + (r * OLD + c0 + 8) * 2);
         const __half2* a = reinterpret_cast<const __half2*>(&r0);
