@@ -24,6 +24,12 @@ def lib():
                 "CPU or PyTorch fallback for the B200 path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.b200lmd_last_error.restype = ctypes.c_char_p
+        # A/B switches between kernel generations for measurements / bisection (all default to the fastest correct
+        # variant): B200_OPT_GEMM_V2=0, B200_OPT_GEMM_V3=0, B200_OPT_ATTN_V2=0, B200_OPT_FUSED_LOSS_STAGE=1
+        for name in ("gemm_v2", "gemm_v3", "attn_v2", "fused_loss_stage"):
+            v = os.environ.get("B200_OPT_" + name.upper())
+            if v is not None:
+                _lib.b200lmd_set_option(name.encode(), ctypes.c_int(int(v)))
     return _lib
 
 
