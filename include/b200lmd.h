@@ -255,6 +255,10 @@ int b200lmd_boxdiff_loss(const b200lmd_boxdiff* p, int B, void* stream);
  * graphs).  After a faulted launch call this to re-zero it (host-synchronous). */
 int b200lmd_xattn_fused_reset(void);
 
+/* profiling aid: launches an EMPTY kernel with the fused kernel's launch configuration (ctas CTAs in clusters of 4, 192
+ * threads, the dynamic shared memory of the head_dim instantiation); bench.py times it for the launch + drain floor */
+int b200lmd_xattn_fused_launch_floor(int head_dim, int ctas, void* stream);
+
 /* profiling aid: device buffer [grid][8] of %globaltimer stamps written by the fused kernel (NULL disables) */
 int b200lmd_set_debug_buffer(void* p);
 

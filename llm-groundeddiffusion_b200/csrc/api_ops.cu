@@ -222,15 +222,53 @@ static int gn_rows_per(int B, int n) {
   return rp < 4 ? 4 : rp;
 }
 
+// GroupNorm reduction scratch (per device, allocated once): block partials + one ticket counter per image.  The
+// counters reset themselves at the end of every launch; launches on one stream are serial, which is the only use here.
+constexpr int kGnPartFloats = 1 << 20;
+constexpr int kGnCounters = 1 << 16;
+struct GnScratch {
+  float* part = nullptr;
+  int* counter = nullptr;
+};
+static GnScratch& gn_scratch(cudaStream_t st) {
+  static GnScratch per_dev[64];
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) throw std::runtime_error("GroupNorm: device index out of range");
+  GnScratch& s = per_dev[dev];
+  if (!s.part) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    B200_CHECK(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone)
+      throw std::runtime_error("GroupNorm: first use inside stream capture - run the launch sequence once eagerly "
+                               "before capturing it");
+    B200_CHECK(cudaMalloc(&s.part, sizeof(float) * kGnPartFloats));
+    B200_CHECK(cudaMalloc(&s.counter, sizeof(int) * kGnCounters));
+    B200_CHECK(cudaMemset(s.counter, 0, sizeof(int) * kGnCounters));
+  }
+  return s;
+}
+static size_t gn_reduce_smem(int C) {
+  const int vecs = C >> 3, tpr = vecs < 256 ? vecs : 256, rif = 256 / tpr;
+  size_t b = sizeof(float) * 2 * rif * C;
+  return b < 1024 ? 1024 : b;
+}
+static void gn_check_scratch(int B, int chunks, int groups) {
+  if ((long long)B * chunks * groups * 2 > kGnPartFloats || B > kGnCounters || groups * 8 > 256)
+    throw std::runtime_error("GroupNorm: batch x chunks x groups exceeds the reduction scratch");
+}
+
 extern "C" int b200lmd_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* sums, int B,
                                      int n, int C, int groups, float eps, int silu, void* stream) {
   return guarded([&] {
     cudaStream_t st = (cudaStream_t)stream;
     if (C % 8 || C % groups) throw std::runtime_error("GroupNorm: C must be a multiple of 8 and of groups");
-    B200_CHECK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * B * groups, st));
     const int rp = gn_rows_per(B, n);
     dim3 grid((n + rp - 1) / rp, B);
-    gn_stats_kernel<<<grid, 256, groups * 2 * sizeof(float), st>>>((const __half*)x, (float*)sums, n, C, groups, rp);
+    GnScratch& gs = gn_scratch(st);
+    gn_check_scratch(B, grid.x, groups);
+    gn_stats_kernel<<<grid, 256, gn_reduce_smem(C), st>>>((const __half*)x, (float*)sums, gs.part, gs.counter, n, C,
+                                                          groups, rp);
     if (2 * C * sizeof(float) > 48 * 1024) throw std::runtime_error("GroupNorm: C too large for the scale/shift table");
     gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>((const __half*)x, (const float*)sums,
                                                               (const float*)gamma, (const float*)beta, (__half*)y, B, n,
@@ -244,13 +282,14 @@ extern "C" int b200lmd_groupnorm_bwd_f16(const void* dy, const void* x, const vo
                                          float eps, int silu, int accumulate, void* stream) {
   return guarded([&] {
     cudaStream_t st = (cudaStream_t)stream;
-    B200_CHECK(cudaMemsetAsync(bsums, 0, sizeof(float) * 2 * B * groups, st));
+    if (C % 8 || C % groups) throw std::runtime_error("GroupNorm: C must be a multiple of 8 and of groups");
     const int rp = gn_rows_per(B, n);
     dim3 grid((n + rp - 1) / rp, B);
-    gn_bwd_stats_kernel<<<grid, 256, groups * 2 * sizeof(float), st>>>((const __half*)dy, (const __half*)x,
-                                                                      (const float*)sums, (const float*)gamma,
-                                                                      (const float*)beta, (float*)bsums, n, C, groups,
-                                                                      eps, silu, rp);
+    GnScratch& gs = gn_scratch(st);
+    gn_check_scratch(B, grid.x, groups);
+    gn_bwd_stats_kernel<<<grid, 256, gn_reduce_smem(C), st>>>((const __half*)dy, (const __half*)x, (const float*)sums,
+                                                              (const float*)gamma, (const float*)beta, (float*)bsums,
+                                                              gs.part, gs.counter, n, C, groups, eps, silu, rp);
     gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(
         (const __half*)dy, (const __half*)x, (const float*)sums, (const float*)bsums, (const float*)gamma,
         (const float*)beta, (__half*)dx, B, n, C, groups, eps, silu, accumulate, rp);

@@ -42,21 +42,57 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// stats[b, g] = (sum, sumsq) over n rows x cpg channels, accumulated with one atomic per (block, group).
+// stats[b, g] = (sum, sumsq) over n rows x cpg channels.  Bit-reproducible from run to run: no floating-point
+// atomics anywhere - per-thread channel sums go to shared memory, one thread per (group, moment) folds them in a fixed
+// order, the block partial is stored to part[b][chunk][group][2], and the last block of the image to finish (ticket on
+// counter[b], self-resetting) adds the chunks in index order into sums[b].  Nothing needs zeroing before the launch.
 // grid = (chunks, B); each block walks rows [chunk*rows_per, ...) of image b with threads over 8-channel vectors.
-__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ sums, int n, int C, int groups,
-                                int rows_per) {
-  extern __shared__ float sacc[];  // [groups][2]
+// dynamic shared memory: 2 * rif * C floats (rif = rows in flight per block).
+__device__ __forceinline__ void gn_fold_and_publish(float* sch, int rifC, int rif, int C, int cpg, int groups,
+                                                    float* __restrict__ part, int* __restrict__ counter,
+                                                    float* __restrict__ out) {
+  __shared__ int s_last;
+  const int b = blockIdx.y, G2 = groups * 2, chunks = gridDim.x;
+  for (int i = threadIdx.x; i < G2; i += blockDim.x) {
+    const int g = i >> 1;
+    const float* src = sch + (i & 1) * rifC + g * cpg;
+    float acc = 0.f;
+    for (int tr = 0; tr < rif; ++tr)
+      for (int c = 0; c < cpg; ++c) acc += src[tr * C + c];
+    part[((long long)b * chunks + blockIdx.x) * G2 + i] = acc;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&counter[b], 1) == chunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // four threads per output, each over every fourth chunk (loads in flight together), combined in a fixed order
+  for (int idx = threadIdx.x; idx < G2 * 4; idx += blockDim.x) {
+    const int i = idx >> 2;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int ch = idx & 3; ch < chunks; ch += 4) acc += __ldcg(&part[((long long)b * chunks + ch) * G2 + i]);
+    sch[idx] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G2; i += blockDim.x)
+    out[(long long)b * G2 + i] = ((sch[4 * i] + sch[4 * i + 1]) + sch[4 * i + 2]) + sch[4 * i + 3];
+  if (threadIdx.x == 0) counter[b] = 0;
+}
+
+__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ sums, float* __restrict__ part,
+                                int* __restrict__ counter, int n, int C, int groups, int rows_per) {
+  extern __shared__ float sch[];  // [2][rif][C] per-thread channel sums
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int vecs = C >> 3;
   const int r0 = blockIdx.x * rows_per;
   const int r1 = min(n, r0 + rows_per);
   // threads as (rows in flight) x (8-channel vectors of a row): every thread streams, loads of a warp are contiguous
   const int tpr = min(vecs, (int)blockDim.x);
   const int rif = blockDim.x / tpr;
+  const int rifC = rif * C;
   const int tr = threadIdx.x / tpr, tv = threadIdx.x - tr * tpr;
   for (int v = tv; v < vecs && tr < rif; v += tpr) {
     float s[8], q[8];
@@ -74,27 +110,14 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
         q[i] += f[i] * f[i];
       }
     }
-    // fold the 8 lanes-of-channel into their groups (an 8-vector straddles at most two groups when cpg >= 8;
-    // for cpg < 8 each element is binned separately)
-    int g_prev = (v * 8) / cpg;
-    float ss = 0.f, qq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (v * 8 + i) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&sacc[g_prev * 2], ss);
-        atomicAdd(&sacc[g_prev * 2 + 1], qq);
-        ss = qq = 0.f;
-        g_prev = g;
-      }
-      ss += s[i];
-      qq += q[i];
-    }
-    atomicAdd(&sacc[g_prev * 2], ss);
-    atomicAdd(&sacc[g_prev * 2 + 1], qq);
+    float* d = sch + tr * C + v * 8;
+    *reinterpret_cast<float4*>(d) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(d + rifC) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(d + rifC + 4) = make_float4(q[4], q[5], q[6], q[7]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&sums[(long long)b * groups * 2 + i], sacc[i]);
+  gn_fold_and_publish(sch, rifC, rif, C, cpg, groups, part, counter, sums);
 }
 
 // y = silu?( (x - mean) * rstd * gamma + beta ), fp16 out.  sums -> mean/rstd on the fly.
@@ -152,19 +175,19 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
 // where dyh = dy * silu'(pre) (pre = xhat*gamma+beta) when do_silu.
 __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half* __restrict__ x,
                                     const float* __restrict__ sums, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, float* __restrict__ bsums, int n, int C,
-                                    int groups, float eps, int do_silu, int rows_per) {
-  extern __shared__ float sacc[];
+                                    const float* __restrict__ beta, float* __restrict__ bsums,
+                                    float* __restrict__ part, int* __restrict__ counter, int n, int C, int groups,
+                                    float eps, int do_silu, int rows_per) {
+  extern __shared__ float sch[];  // [2][rif][C], reduced in a fixed order like gn_stats_kernel
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int vecs = C >> 3;
   const int r0 = blockIdx.x * rows_per;
   const int r1 = min(n, r0 + rows_per);
   const float inv_cnt = 1.f / ((float)n * cpg);
   const int tpr = min(vecs, (int)blockDim.x);
   const int rif = blockDim.x / tpr;
+  const int rifC = rif * C;
   const int tr = threadIdx.x / tpr, tv = threadIdx.x - tr * tpr;
   for (int v = tv; v < vecs && tr < rif; v += tpr) {
     float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
@@ -196,15 +219,14 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ dy, const __half*
         s2[j] += d * xh;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
-      atomicAdd(&sacc[g * 2], s1[j]);
-      atomicAdd(&sacc[g * 2 + 1], s2[j]);
-    }
+    float* d = sch + tr * C + v * 8;
+    *reinterpret_cast<float4*>(d) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+    *reinterpret_cast<float4*>(d + rifC) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    *reinterpret_cast<float4*>(d + rifC + 4) = make_float4(s2[4], s2[5], s2[6], s2[7]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&bsums[(long long)b * groups * 2 + i], sacc[i]);
+  gn_fold_and_publish(sch, rifC, rif, C, cpg, groups, part, counter, bsums);
 }
 
 // backward, pass 2: dx = rstd * (d - mean(d) - xhat * mean(d * xhat)),  d = dyh*gamma ; dx (+)= into out
