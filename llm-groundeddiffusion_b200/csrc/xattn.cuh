@@ -110,10 +110,36 @@ struct LossStaged {
   const uint8_t* mk;   // [n_terms][n]
 };
 
+// 8 mask bytes (one per element of a lane's block) -> bit j set when byte j is non-zero
+__device__ __forceinline__ uint64_t loss_mask_bits8(uint64_t raw) {
+  uint64_t m = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if ((raw >> (8 * j)) & 0xFFull) m |= 1ull << j;
+  return m;
+}
+// true when the lane's 8 values / 8 mask bytes of an energy problem can be fetched with three vector loads
+__device__ __forceinline__ bool loss_vec_ok(const LossProb& P, int n, int per, int i0) {
+  return per == 8 && i0 + 8 <= n && !P.R && !P.staged &&
+         (((uintptr_t)(P.src + i0) & 15) | ((uintptr_t)(P.mk + i0) & 7)) == 0;
+}
+
 template <int PERMAX>
 __device__ __forceinline__ void loss_load(LossRaw<PERMAX>& q, const LossProb& P, int n, int per, int lane) {
   const int i0 = lane * per;
   q.m = 0ull;
+  if (PERMAX == 8 && loss_vec_ok(P, n, per, i0)) {
+    // n = 256 (the guidance resolution of SD1.x at 512^2): the lane's 8 values and 8 mask bytes are three vector loads
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(P.src + i0));
+    const float4 c = __ldcg(reinterpret_cast<const float4*>(P.src + i0) + 1);
+    const uint2 mb = *reinterpret_cast<const uint2*>(P.mk + i0);
+    q.v[0] = a.x; q.v[1] = a.y; q.v[2] = a.z; q.v[3] = a.w;
+    q.v[4] = c.x; q.v[5] = c.y; q.v[6] = c.z; q.v[7] = c.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q.r[j] = 0.f;
+    q.m = loss_mask_bits8(((uint64_t)mb.y << 32) | mb.x);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < PERMAX; ++j) {
     const int i = i0 + j;
@@ -298,11 +324,21 @@ template <int PERMAX, bool PIPE>
 __device__ __forceinline__ void loss_problem_loop(const XattnLoss& L, const LossTerm* sterms, const int* stok,
                                                   const unsigned short* pcode, float* prob_loss, float* dpx, int n_prob,
                                                   int first, int stride, int lane, int bh, int h, int heads, int n,
-                                                  int per, const LossStaged& stg) {
+                                                  int per, const LossStaged& stg, const LossRaw<PERMAX>& pre,
+                                                  bool have_pre) {
   if (first >= n_prob) return;
   LossProb P = loss_decode(L, sterms, stok, pcode[first], bh, h, heads, n, stg);
   LossRaw<PERMAX> cur;
-  loss_load(cur, P, n, per, lane);
+  if (have_pre) {                                          // first problem's inputs already requested by the caller
+#pragma unroll
+    for (int j = 0; j < PERMAX; ++j) {
+      cur.v[j] = pre.v[j];
+      cur.r[j] = 0.f;
+    }
+    cur.m = loss_mask_bits8(pre.m);                        // loss_prefetch_first leaves the 8 raw mask bytes here
+  } else {
+    loss_load(cur, P, n, per, lane);
+  }
   for (int pid = first; pid < n_prob; pid += stride) {
     const bool more = pid + stride < n_prob;
     LossProb Pn = P;
@@ -396,14 +432,52 @@ __device__ __forceinline__ void loss_zero(const XattnLoss& L, int bh, int n, int
   for (int i = tid; i < tot; i += 128) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Request the inputs of this warp's FIRST problem (the loads loss_run would start with) - for callers that have
+// something else to do between "the P columns are published" and loss_run (the fused kernel: a cluster barrier).
+// Only issues loads: nothing here consumes a loaded value (out.m holds the 8 RAW mask bytes, decoded by the consumer),
+// so the calling warp does not wait for the round trip.  Returns false when there is nothing to prefetch or the
+// three-vector-load layout does not apply (reference terms, n != 256); then loss_run loads as usual.
+__device__ __forceinline__ bool loss_prefetch_first(const XattnLoss& L, float* scratch, int tid, int h, int heads, int bh,
+                                                    int n, int part, int nparts, LossRaw<8>& out) {
+  const int warp = tid >> 5, lane = tid & 31;
+  LossScratch S = loss_scratch(scratch);
+  const int per = (n + 31) >> 5;
+  const int first = part * 4 + warp;
+  if (per > 8 || first >= S.n_prob[0]) return false;
+  LossStaged stg;
+  stg.col = nullptr;
+  stg.mk = nullptr;
+  const LossProb P = loss_decode(L, S.sterms, S.stok, S.pcode[first], bh, h, heads, n, stg);
+  const int i0 = lane * per;
+  if (!loss_vec_ok(P, n, per, i0)) return false;           // per-lane condition is warp-uniform: per, n, alignment
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(P.src + i0));
+  const float4 c = __ldcg(reinterpret_cast<const float4*>(P.src + i0) + 1);
+  const uint2 mb = *reinterpret_cast<const uint2*>(P.mk + i0);
+  out.v[0] = a.x; out.v[1] = a.y; out.v[2] = a.z; out.v[3] = a.w;
+  out.v[4] = c.x; out.v[5] = c.y; out.v[6] = c.z; out.v[7] = c.w;
+  out.m = ((uint64_t)mb.y << 32) | mb.x;
+  return true;
+}
+
+// second half of the two-part combine when loss_run was given ticket_out: the later of the two parts resets the counters
+__device__ __forceinline__ void loss_ticket_reset(int ticket, int* done, int* ready, int bh) {
+  // opaque consumer: written in C the comparison is hoisted up to the atomic and waits for its round trip there
+  asm volatile(
+      "{\n .reg .pred p;\n setp.eq.s32 p, %0, 1;\n @p st.global.u32 [%1], 0;\n @p st.global.u32 [%2], 0;\n}" ::"r"(ticket),
+      "l"(done + bh), "l"(ready + bh)
+      : "memory");
+}
+
 #define LOSS_STAMP(i) do { if (dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = t_; } } while (0)
 // part/nparts: the problems are dealt round-robin to nparts CTAs x 4 warps.  With nparts > 1 every CTA leaves its
 // partial in partials[bh*nparts + part] and the last one to arrive (done[bh]) adds them up in part order, so the sum
 // does not depend on arrival order.  done[bh] must be zero on entry and is zero again on exit (so is ready[bh]).
-__device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int tid, int h, int heads, int bh, int n,
+__device__ __forceinline__ int loss_run(const XattnLoss& L, float* scratch, int tid, int h, int heads, int bh, int n,
                                          int part, int nparts, float* partials, int* done,
-                                         unsigned long long* dbg = nullptr, int* ready = nullptr,
-                                         uint8_t* stage = nullptr, int stage_bytes = 0) {
+                                         unsigned long long* dbg, int* ready,
+                                         uint8_t* stage, int stage_bytes, bool defer_ticket, const LossRaw<8>& pre,
+                                         bool have_pre) {
+  int ticket = -1;                                         // returned when defer_ticket: see loss_ticket_reset
   const int warp = tid >> 5, lane = tid & 31;
   LossScratch S = loss_scratch(scratch);
   const int n_prob = S.n_prob[0];
@@ -436,10 +510,12 @@ __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int
   }
   if (per <= 8)
     loss_problem_loop<8, true>(L, S.sterms, S.stok, S.pcode, S.prob_loss, dpx, n_prob, part * 4 + warp, 4 * nparts,
-                               lane, bh, h, heads, n, per, stg);
-  else
+                               lane, bh, h, heads, n, per, stg, pre, have_pre && !stg.col);
+  else {
+    LossRaw<40> none;
     loss_problem_loop<40, false>(L, S.sterms, S.stok, S.pcode, S.prob_loss, dpx, n_prob, part * 4 + warp, 4 * nparts,
-                                 lane, bh, h, heads, n, per, stg);
+                                 lane, bh, h, heads, n, per, stg, none, false);
+  }
   LOSS_STAMP(1);
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (tid == 0) {                                          // fixed summation order => deterministic loss
@@ -453,7 +529,11 @@ __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int
       // two parts: loss_part[bh] was zeroed by part 0 before the hand-shake; 0 + a + b is the same float in either
       // arrival order, so two fire-and-forget atomics replace the store / fence / ticket / re-read chain
       atomicAdd(L.loss_part + bh, acc);
-      if (atomicAdd(done + bh, 1) == 1) {
+      if (defer_ticket) {
+        // the caller consumes the ticket later (loss_ticket_reset), so that this thread's warp - and everybody behind
+        // the next barrier - does not sit out the atomic's round trip here
+        ticket = atomicAdd(done + bh, 1);
+      } else if (atomicAdd(done + bh, 1) == 1) {
         done[bh] = 0;                                      // both parts are past their wait on `ready` by now
         if (ready) ready[bh] = 0;
       }
@@ -471,6 +551,7 @@ __device__ __forceinline__ void loss_run(const XattnLoss& L, float* scratch, int
     }
   }
   LOSS_STAMP(2);
+  return ticket;
 }
 
 // everything at once (unfused kernel: the last CTA of the (image, head) does it all)
@@ -479,7 +560,8 @@ __device__ __forceinline__ void xattn_loss_reduce(const XattnLoss& L, float* scr
   loss_zero(L, bh, n, 0, n, tid);
   __threadfence_block();
   loss_stage(L, scratch, tid, b);       // its barriers also order the zero-fill before the atomics
-  loss_run(L, scratch, tid, h, heads, bh, n, 0, 1, nullptr, nullptr);
+  LossRaw<8> none;
+  loss_run(L, scratch, tid, h, heads, bh, n, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, false, none, false);
   (void)s_red;
 }
 

@@ -242,6 +242,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     return __half2float(chunk[t & 7]);
   };
   float row_m = 0.f, row_l = 1.f;
+  LossRaw<8> loss_pre;                            // first loss problem of this warp, requested before the cluster barrier
+  bool loss_have_pre = false;
   if (warp >= 2) {
     // loss inputs while phase 1 runs on the tensor core: this tile's rows of dp_extra zeroed (ordered before every
     // CTA's atomics by the publish fence below), term / slot tables and the problem list staged in shared memory
@@ -342,8 +344,9 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (t >= 0) p.probs_tok[(long long)bh * p.n + tok] = __float2half_rn(p_at(t));
     }
     if (p.has_loss) {
+      const int* stok = loss_scratch(sL).stok;         // staged by loss_stage above (no global round trip per slot)
       for (int s = 0; s < kMaxSlots; ++s) {
-        const int t = p.L.slot_tok[b * kMaxSlots + s];
+        const int t = stok[s];
         if (t < 0) break;
         p.L.pcol[((long long)bh * kMaxSlots + s) * p.n + tok] = p_at(t);
       }
@@ -357,9 +360,36 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     mbar_wait(acc_full, 0);   // third completion of acc_full: parity 0 again
     tc_fence_after();
     FUSED_STAMP(3);
+    constexpr int OLD = D + 8;                         // padded row stride (halves)
+    {
+      // inputs of the OUTPUT epilogue, fetched now: the K/V region is dead (S and P.V have completed), so the residual
+      // tile (asynchronous LDGSTS copies, waited for only before the output epilogue) and this head's slice of the
+      // output-projection bias land there while the hand-shake, the cluster barrier and phase 2 run
+      constexpr int PPR = D / 8;
+      static_assert(128 * (D + 8) * 2 <= Cfg::K_BYTES + Cfg::V_BYTES, "residual staging must fit in the K/V region");
+      static_assert(128 * (D + 8) * 2 + 1024 <= Cfg::K_BYTES + Cfg::V_BYTES && D * 4 <= 1024, "bias staging must fit");
+      const uint32_t stgE_s = smem_u32(sK);
+      if (p.residual) {
+        for (int pi = tid; pi < 128 * PPR; pi += 128) {
+          const int row = pi / PPR, pc = pi - row * PPR;
+          const __half* src = p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stgE_s + (row * OLD + pc * 8) * 2), "l"(src)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if (tid < D / 4) {
+        const uint32_t dst = smem_u32(sK + Cfg::K_BYTES + Cfg::V_BYTES - 1024) + tid * 16;
+        if (p.bias_o) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.bias_o + h * D + tid * 4) : "memory");
+        } else {
+          sts128(dst, make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     // stage the row in shared memory (ring scratch: Q / P are dead once P.V has completed), then leave as full row
     // segments: consecutive lanes write consecutive 16-byte pieces of a row
-    constexpr int OLD = D + 8;                         // padded row stride (halves)
     __half* stgO = reinterpret_cast<__half*>(ring);
     const uint32_t stgO_s = smem_u32(stgO);
 #pragma unroll 1
@@ -421,7 +451,13 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   // every CTA of the cluster has left the core (ring scratch free) and all 8 O_h of the row tile are visible
   __syncwarp();
   FUSED_STAMP(4);
-  cluster_sync_all();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  // every tile's P columns of this (image, head) are published and fenced (thread 0 saw bh_ready complete, then the
+  // CTA barrier above): request the first loss problem's inputs between arrive and wait, so that their L2 round trip
+  // runs under the cluster barrier (after the arrive: its release fence would otherwise wait for these loads)
+  if (warp >= 2 && p.has_loss && !fused_loss_stage_enabled(p))
+    loss_have_pre = loss_prefetch_first(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, loss_pre);
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   FUSED_STAMP(5);
 
@@ -461,38 +497,25 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else {
     constexpr int OLD = D + 8;
     constexpr int PPR = D / 8;
-    // residual tile -> shared memory WHILE phase 2 runs on the tensor core (these warps are idle until the accumulator
-    // is complete).  It lands in the K/V region, dead since the core; loads are batched so they overlap each other.
+    // the residual tile and the bias slice were requested right after the core (K/V region); nothing has waited on
+    // them yet
     __half* stgE = reinterpret_cast<__half*>(sK);
     const uint32_t stgE_s = smem_u32(stgE);
-    static_assert(128 * (D + 8) * 2 <= Cfg::K_BYTES + Cfg::V_BYTES, "residual staging must fit in the K/V region");
-    // output-projection bias of this head -> shared memory now (while phase 2 runs), so the epilogue loop below does not
-    // pay a global-load round trip per 16-column step
-    float* s_bias = reinterpret_cast<float*>(sK + Cfg::K_BYTES + Cfg::V_BYTES - 1024);
-    static_assert(128 * (D + 8) * 2 + 1024 <= Cfg::K_BYTES + Cfg::V_BYTES && D * 4 <= 1024, "bias staging must fit");
-    for (int i = tid; i < D; i += 128) s_bias[i] = p.bias_o ? __ldg(p.bias_o + h * D + i) : 0.f;
-    if (p.residual) {
-      // asynchronous copies (LDGSTS): nothing waits on them until the accumulator is needed
-      for (int pi = tid; pi < 128 * PPR; pi += 128) {
-        const int row = pi / PPR, pc = pi - row * PPR;
-        const __half* src = p.residual + ((long long)row0 + row) * p.C + h * D + pc * 8;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stgE_s + (row * OLD + pc * 8) * 2), "l"(src)
-                     : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    const float* s_bias = reinterpret_cast<const float*>(sK + Cfg::K_BYTES + Cfg::V_BYTES - 1024);
     // ---- guidance loss, overlapped with phase 2 on the tensor core: the row tiles of this (image, head) share the
     // problems once every tile's P columns are published (fenced before bh_ready went up)
+    int loss_ticket = -1;
     if (p.has_loss) {
       // every tile's P columns are published: thread 0 saw bh_ready complete (and fenced) before the cluster barrier
       // staging area: the K/V region behind the residual / output staging rows (dead since the core)
       uint8_t* lstage = sK + 128 * OLD * 2;
       const int lstage_bytes = Cfg::K_BYTES + Cfg::V_BYTES - 128 * OLD * 2 - 1024;   // the last KB holds the bias
-      loss_run(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, p.loss_partials, p.bh_done,
-               p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr, p.bh_ready,
-               fused_loss_stage_enabled(p) ? lstage : nullptr, lstage_bytes);
+      loss_ticket = loss_run(p.L, sL, tid, h, 8, bh, p.n, tok0 >> 7, p.tiles_per_img, p.loss_partials, p.bh_done,
+                             p.dbg ? p.dbg + (long long)blockIdx.x * 16 + 8 : nullptr, p.bh_ready,
+                             fused_loss_stage_enabled(p) ? lstage : nullptr, lstage_bytes, p.tiles_per_img == 2,
+                             loss_pre, loss_have_pre);
     }
-    if (p.residual) asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("bar.sync 1, 128;" ::: "memory");       // residual tile and bias are in shared memory
     mbar_wait(acc_full, 1);   // fourth completion
     tc_fence_after();
@@ -528,7 +551,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           lds128(stgE_s + (row * OLD + pc * 8) * 2);
     }
     tc_fence_before();
-
+    // two-part loss combine: the ticket was taken inside loss_run (thread 0), its round trip has long returned
+    if (p.has_loss && tid == 0 && p.tiles_per_img == 2) loss_ticket_reset(loss_ticket, p.bh_done, p.bh_ready, bh);
   }
   FUSED_STAMP(7);
   __syncthreads();
