@@ -264,7 +264,10 @@ int b200lmd_set_debug_buffer(void* p);
 
 /* ------------------------------------------------------------------------------------------------ normalisation
  * GroupNorm (+ optional SiLU) over NHWC fp16 x[B, n, C]: stats then apply (torch.nn.GroupNorm inside diffusers
- * ResnetBlock2D and models/transformer_2d.py:146,283).  sums: fp32 [B, groups, 2] scratch (zeroed by the call). */
+ * ResnetBlock2D and models/transformer_2d.py:146,283).  sums: fp32 [B, groups, 2] (sum, sum of squares) per group,
+ * written by the call (kept for the backward).  The reduction runs in a fixed order through a per-device scratch that
+ * the library allocates on first use (outside stream capture): results repeat bit for bit; launches that share a
+ * device must be ordered on one stream, like every other entry point here. */
 int b200lmd_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, void* sums, int B, int n, int C,
                           int groups, float eps, int silu, void* stream);
 int b200lmd_groupnorm_bwd_f16(const void* dy, const void* x, const void* sums, const void* gamma, const void* beta,
