@@ -100,10 +100,17 @@ class SyntheticEnv:
 class ReferenceEnv:
     """adapter over the reference's model_dict (tokenizer, text_encoder, vae[, sam]) - see INTEGRATION.md"""
 
-    def __init__(self, model_dict, refine_mask=None, device="cuda"):
+    def __init__(self, model_dict, refine_mask=None, device="cuda", sam_predict=None, sam_kwargs=None):
+        """refine_mask: a complete replacement of the SAM step, `f(image, box, token_attn) -> [H, W] mask`;
+        sam_predict: only the SAM network, `f(image, input_boxes=None, input_points=None) -> (three masks at image
+        resolution, three predicted IoUs)` - prompt construction and candidate selection then run in mask_refine.py
+        (`sam_predict_from(model_dict)` wraps the reference's own sam_model / sam_processor); sam_kwargs: overrides of the
+        thresholds (mask_refine.refine_attn / refine_box keyword arguments)"""
         self.md = model_dict
         self.device = device
         self._refine = refine_mask
+        self._sam_predict = sam_predict
+        self._sam_kwargs = dict(sam_kwargs or {})
 
     def _token_map(self, prompt):
         ids = self.md.tokenizer([prompt], padding="do_not_pad", max_length=77, return_tensors="np")["input_ids"][0]
@@ -157,4 +164,31 @@ class ReferenceEnv:
         LMD prompts SAM with points from `token_attn`, LMD+ with the box).  Without a callable: the box raster."""
         if self._refine is not None:
             return torch.as_tensor(self._refine(image, box, token_attn)).bool()
+        if self._sam_predict is not None:
+            from . import mask_refine as MR
+            height, width = int(image.shape[0]), int(image.shape[1])
+            if token_attn is not None:      # LMD: models/sam.py sam_refine_attn
+                m, _ = MR.refine_attn(self._sam_predict, image, np.asarray(torch.as_tensor(token_attn).cpu()), height, width,
+                                      H, W, **self._sam_kwargs)
+            else:                           # LMD+: models/sam.py sam_refine_box
+                m, _ = MR.refine_box(self._sam_predict, image, box, height, width, H, W, **self._sam_kwargs)
+            return torch.as_tensor(m).bool()
         return box_to_mask(box, H, W).bool()
+
+
+def sam_predict_from(model_dict, device="cuda"):
+    """the SAM network call of models/sam.py:25-47 as a `sam_predict` hook over the reference's own
+    `model_dict["sam_model"]` / `model_dict["sam_processor"]` (transformers SamModel / SamProcessor - third-party, not
+    part of this library): three candidate masks at image resolution + their predicted IoUs for one image / one prompt"""
+    model, proc = model_dict["sam_model"], model_dict["sam_processor"]
+
+    @torch.no_grad()
+    def predict(image, input_boxes=None, input_points=None):
+        with torch.autocast(device):
+            inputs = proc(image, input_points=input_points, input_boxes=input_boxes, return_tensors="pt").to(device)
+            outputs = model(**inputs)
+        masks = proc.image_processor.post_process_masks(outputs.pred_masks.cpu().float(), inputs["original_sizes"].cpu(),
+                                                        inputs["reshaped_input_sizes"].cpu())
+        return masks[0][0], outputs.iou_scores.cpu().numpy()[0, 0]
+
+    return predict

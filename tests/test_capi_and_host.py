@@ -272,3 +272,45 @@ def test_guidance_step_scale_branches():
     assert abs(guidance_step_scale(s, 3, t) - float((1 - s.alphas_cumprod[t]) ** 0.5)) < 1e-12
     s.sigmas = np.linspace(14.6, 0.0, 51)
     assert abs(guidance_step_scale(s, 3, t) - float(s.sigmas[3]) ** 2) < 1e-12
+
+
+def test_env_refine_mask_with_sam_predict_hook():
+    """ReferenceEnv(sam_predict=...): prompt construction and candidate selection run in mask_refine, only the network
+    call is the hook (models/sam.py; the bit-exact comparison with the reference lives in test_oracle_vs_reference.py)"""
+    import numpy as np
+    import torch
+    from lgd_b200 import mask_refine as MR
+    from lgd_b200.env import ReferenceEnv
+    calls = []
+
+    def predict(image, input_boxes=None, input_points=None):
+        calls.append((input_boxes, input_points))
+        yy, xx = np.mgrid[0:512, 0:512]
+        if input_boxes is not None:
+            b = input_boxes[0]
+            x0, y0, x1, y1 = b if np.ndim(b) == 1 else b[0]
+        else:
+            px, py = input_points[0][0]
+            x0, y0, x1, y1 = px - 64, py - 64, px + 64, py + 64
+        inside = (xx >= x0) & (xx < x1) & (yy >= y0) & (yy < y1)
+        small = inside & (xx < (x0 + x1) / 2)
+        return np.stack([inside, small, np.ones_like(inside)]), np.array([0.95, 0.99, 0.5], dtype=np.float32)
+
+    env = ReferenceEnv(model_dict=None, sam_predict=predict)
+    image = np.zeros((512, 512, 3), dtype=np.uint8)
+    box = (0.25, 0.25, 0.75, 0.5)
+    m = env.refine_mask(image, box, 64, 64)                       # LMD+: box prompt in pixels
+    assert calls[-1][0] == [[[128, 128, 384, 256]]] and calls[-1][1] is None
+    assert m.dtype == torch.bool and m.shape == (64, 64)
+    # candidate 2 (everything) has confidence 0.5 < 0.85 and is pushed back; candidate 0 (the box) is the largest left
+    assert int(m.sum()) >= 32 * 16 and not bool(m[0, 0])
+    attn = np.zeros((16, 16), dtype=np.float32)
+    attn[8, 4] = 1.0
+    m2 = env.refine_mask(image, box, 64, 64, token_attn=torch.from_numpy(attn))     # LMD: point prompt at the arg-max
+    assert calls[-1][0] is None and calls[-1][1] == [[[4 * 32, 8 * 32]]]
+    assert m2.shape == (64, 64) and bool(m2[8 * 4, 4 * 4])
+    attn[6:11, 3:9] = 1.0                                         # a blob survives the binary opening of the box path
+    mb, prompt = MR.attn_prompt(attn, 512, 512, use_box_input=True)
+    assert list(prompt) == ["input_boxes"] and len(prompt["input_boxes"][0]) == 4
+    with __import__("pytest").raises(ValueError):
+        MR.binary_mask_to_box(np.zeros((4, 4), dtype=bool))

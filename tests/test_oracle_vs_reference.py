@@ -379,3 +379,132 @@ def test_boxdiff_loop_matches_reference():
                                boxdiff=dict(bboxes=bboxes, object_positions=positions, keys=keys, max_index_step=3))
     assert len(res["boxdiff_losses"]) == 3
     assert (res["latents"] - lat_ref).abs().max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mask refinement around the SAM network: lgd_b200.mask_refine vs the UNMODIFIED models/sam.py, both
+# driven by the same synthetic "SAM network" (three candidate masks + predicted IoUs as a function of the prompt)
+def _fake_prompt(input_boxes, input_points):
+    if input_boxes is not None:          # [[[4]]] from sam_refine_boxes, [[4]] from sam_refine_attn (models/sam.py:141-142)
+        b = input_boxes[0]
+        return "box", (b if np.ndim(b) == 1 else b[0])
+    return "point", input_points[0][0]
+
+
+def _fake_sam_candidates(prompt_kind, prompt, size=512, seed=0):
+    """deterministic stand-in for facebook/sam-vit-base: candidates grown from the prompt (whole / part / over-grown
+    object, the usual three granularities), scores from a seeded generator"""
+    rng = np.random.RandomState(seed + int(sum(np.ravel(prompt))) % 9973)
+    yy, xx = np.mgrid[0:size, 0:size]
+    if prompt_kind == "box":
+        x0, y0, x1, y1 = [float(v) for v in prompt]
+    else:
+        px, py = [float(v) for v in prompt]
+        w, h = rng.uniform(60, 200), rng.uniform(60, 200)
+        x0, y0, x1, y1 = px - w / 2, py - h / 2, px + w / 2, py + h / 2
+    cx, cy, rx, ry = (x0 + x1) / 2, (y0 + y1) / 2, max((x1 - x0) / 2, 2.0), max((y1 - y0) / 2, 2.0)
+    ell = lambda s: (((xx - cx) / (rx * s)) ** 2 + ((yy - cy) / (ry * s)) ** 2) <= 1.0
+    masks = np.stack([ell(0.9), ell(0.45) & (yy < cy), ell(rng.uniform(1.3, 2.5))])
+    scores = rng.uniform(0.7, 1.0, size=3).astype(np.float32)
+    return masks, scores
+
+
+class _FakeSamInputs(dict):
+    def to(self, device):
+        return self
+
+
+class _FakeSamProcessor:
+    def __init__(self, seed):
+        self.seed = seed
+        self.image_processor = self
+
+    def __call__(self, image, input_points=None, input_boxes=None, return_tensors="pt"):
+        kind, prompt = _fake_prompt(input_boxes, input_points)
+        if isinstance(image, list):                      # sam_refine_boxes hands over a list of images
+            image = image[0]
+        masks, scores = _fake_sam_candidates(kind, prompt, size=np.asarray(image).shape[0], seed=self.seed)
+        return _FakeSamInputs(masks=torch.from_numpy(masks), scores=torch.from_numpy(scores),
+                              original_sizes=torch.tensor([[masks.shape[1], masks.shape[2]]]),
+                              reshaped_input_sizes=torch.tensor([[1024, 1024]]))
+
+    def post_process_masks(self, pred_masks, original_sizes, reshaped_input_sizes):
+        return [pred_masks[0] > 0]                       # [n_prompts = 1, 3, h, w] bool per image
+
+
+class _FakeSamModel:
+    def __call__(self, masks, scores, original_sizes, reshaped_input_sizes):
+        import types
+        return types.SimpleNamespace(pred_masks=(masks.float() * 2 - 1)[None, None], iou_scores=scores[None, None])
+
+
+def _fake_predict(seed):
+    def predict(image, input_boxes=None, input_points=None):
+        kind, prompt = _fake_prompt(input_boxes, input_points)
+        return _fake_sam_candidates(kind, prompt, size=np.asarray(image).shape[0], seed=seed)
+    return predict
+
+
+def _ref_sam():
+    ref_loader.load()
+    from models import sam as rsam
+    rsam.torch_device = "cpu"
+    return rsam
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_mask_refine_box_matches_reference_sam(seed):
+    from lgd_b200 import mask_refine as MR
+    rsam = _ref_sam()
+    rng = np.random.RandomState(seed)
+    image = rng.randint(0, 255, size=(512, 512, 3)).astype(np.uint8)
+    md = dict(sam_model=_FakeSamModel(), sam_processor=_FakeSamProcessor(seed))
+    for _ in range(6):
+        x0, y0 = rng.uniform(0, 0.6, size=2)
+        box = (x0, y0, x0 + rng.uniform(0.08, 0.4), y0 + rng.uniform(0.08, 0.4))
+        conf_th, iou_th = rng.choice([0.85, 0.8, 0.95]), rng.choice([0.2, 0.25, 0.6])
+        m_ref, c_ref = rsam.sam_refine_box(image, box, model_dict=md, height=512, width=512, H=64, W=64,
+                                           discourage_mask_below_confidence=conf_th,
+                                           discourage_mask_below_coarse_iou=iou_th, verbose=False)
+        m, c = MR.refine_box(_fake_predict(seed), image, box, 512, 512, 64, 64, discourage_mask_below_confidence=conf_th,
+                             discourage_mask_below_coarse_iou=iou_th)
+        assert m.dtype == np.bool_ and m.shape == (64, 64)
+        assert np.array_equal(m, m_ref) and float(c) == float(c_ref)
+
+
+@pytest.mark.parametrize("use_box_input", [False, True])
+@pytest.mark.parametrize("side", [16, 64])
+def test_mask_refine_attn_matches_reference_sam(use_box_input, side):
+    from lgd_b200 import mask_refine as MR
+    rsam = _ref_sam()
+    rng = np.random.RandomState(10 + side + int(use_box_input))
+    image = rng.randint(0, 255, size=(512, 512, 3)).astype(np.uint8)
+    md = dict(sam_model=_FakeSamModel(), sam_processor=_FakeSamProcessor(5))
+    sigma = MR.GAUSSIAN_SIGMA_BOX_INPUT if use_box_input else MR.GAUSSIAN_SIGMA_POINT_INPUT
+    for _ in range(6):
+        # a token-attention map: a blob plus noise, like utils/attn.py get_token_attnv2 hands over
+        yy, xx = np.mgrid[0:side, 0:side] / side
+        cx, cy, s = rng.uniform(0.25, 0.75), rng.uniform(0.25, 0.75), rng.uniform(0.08, 0.2)
+        attn = (np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s)) + 0.05 * rng.rand(side, side)).astype(np.float32)
+        kw = dict(use_box_input=use_box_input, gaussian_sigma=sigma, mask_th_for_box=0.05, n_erode_dilate_mask_for_box=1,
+                  mask_th_for_point=0.25, discourage_mask_below_confidence=0.85, discourage_mask_below_coarse_iou=0.25)
+        m_ref, c_ref = rsam.sam_refine_attn(image, attn.copy(), model_dict=md, height=512, width=512, H=64, W=64,
+                                            verbose=False, **kw)
+        m, c = MR.refine_attn(_fake_predict(5), image, attn.copy(), 512, 512, 64, 64, **kw)
+        assert np.array_equal(m, m_ref) and float(c) == float(c_ref)
+        mb, prompt = MR.attn_prompt(attn, 512, 512, use_box_input, sigma)
+        assert mb.shape == (side, side) and (("input_boxes" in prompt) == use_box_input)
+
+
+def test_select_mask_rule_matches_reference():
+    from lgd_b200 import mask_refine as MR
+    rsam = _ref_sam()
+    rng = np.random.RandomState(0)
+    for _ in range(50):
+        masks = rng.rand(3, 32, 32) > rng.uniform(0.2, 0.9, size=(3, 1, 1))
+        conf = rng.uniform(0.6, 1.0, size=3)
+        ious = rng.uniform(0.0, 0.6, size=3) if rng.rand() < 0.7 else None
+        a, ca = rsam.select_mask(masks, conf, coarse_ious=ious, discourage_mask_below_confidence=0.85,
+                                 discourage_mask_below_coarse_iou=0.2)
+        b, cb = MR.select_mask(masks, conf, ious, 0.85, 0.2)
+        assert np.array_equal(a, b) and ca == cb
