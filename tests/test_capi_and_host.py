@@ -314,3 +314,22 @@ def test_env_refine_mask_with_sam_predict_hook():
     assert list(prompt) == ["input_boxes"] and len(prompt["input_boxes"][0]) == 4
     with __import__("pytest").raises(ValueError):
         MR.binary_mask_to_box(np.zeros((4, 4), dtype=bool))
+
+
+def test_measurement_helpers_read_committed_profiles():
+    """bench.py takes `roofline.traffic` from the committed ncu export (not a literal), and the launch-list summariser
+    parses the committed ncu CSV of the final tree"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    traffic, src = bench.ncu_dram_traffic()
+    assert src == os.path.join("profiles", "xattn_fused_ncu_raw.csv")
+    assert 15e6 < traffic < 40e6          # x + Wq + Wo + K/V + residual of the roofline shape: ~20.8 MB per launch
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "launches_summary.py"),
+                          os.path.join(root, "profiles", "r2", "launches_step_call12.csv")],
+                         capture_output=True, text=True, check=True).stdout
+    assert "b200::xattn_fused_kernel<160>" in out and "b200::gemm2_tc_kernel" in out
+    assert "this library's kernels" in out.splitlines()[0]
