@@ -170,9 +170,12 @@ def xattn_roofline(dev, with_loss=True):
     flops = B * (2 * n * C * C * 2 + 2 * n * T * C * 2)
     peak, _, how = peaks()
     ach = flops / (ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_dram_traffic()
     out = {"bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
-           "traffic": ncu_dram_traffic()[0], "traffic_source": ncu_dram_traffic()[1], "kernel": "xattn_fused_kernel (projections + attention + guidance loss)",
-           "launches_per_op": 1, "ms_per_op": round(ms, 4), "peak_source": how + " (burst, kernel timed alone before the step loop)",
+           "traffic": traffic, "traffic_source": traffic_src,
+           "kernel": "xattn_fused_kernel (projections + attention + guidance loss)",
+           "launches_per_op": 1, "ms_per_op": round(ms, 4),
+           "peak_source": how + " (burst, kernel timed alone before the step loop)",
            "shape": {"B": B, "n": n, "C": C, "heads": heads, "T": T}}
     if not with_loss:
         return out
@@ -180,13 +183,20 @@ def xattn_roofline(dev, with_loss=True):
     # bracketed the same way = the launch + drain share of ms_per_op; (2) the kernel launched back to back over rotating
     # input sets larger than L2 (8 x (x, Wq, Wo, residual) = 136 MB; outputs from the caching allocator), one event pair
     # around one CUDA-graph replay of 96 launches = its duration inside a stream of kernels (how the step runs it)
-    from lgd_b200._lib import check, cur_stream, lib
     import ctypes
-    floor_ms, _ = isolated(lambda: check(lib().b200lmd_xattn_fused_launch_floor(ctypes.c_int(d), ctypes.c_int(B * n // 128 * heads),
-                                                                                cur_stream())))
+    from lgd_b200._lib import check, cur_stream, lib
+    n_ctas = B * n // 128 * heads
+
+    def null_launch():
+        check(lib().b200lmd_xattn_fused_launch_floor(ctypes.c_int(d), ctypes.c_int(n_ctas), cur_stream()))
+
+    floor_ms, _ = isolated(null_launch)
     sets = [(x.clone(), wq.clone(), wo.clone(), res.clone()) for _ in range(8)]
-    run = lambda i: ops.xattn_fused(sets[i % 8][0], sets[i % 8][1], k, vt, sets[i % 8][2], bo, sets[i % 8][3], B, n, heads, d, T,
-                                    d ** -0.5, loss=kl)
+
+    def run(i):
+        xs, wqs, wos, rs = sets[i % 8]
+        return ops.xattn_fused(xs, wqs, k, vt, wos, bo, rs, B, n, heads, d, T, d ** -0.5, loss=kl)
+
     for i in range(8):
         run(i)
     torch.cuda.synchronize()
