@@ -333,3 +333,33 @@ def test_measurement_helpers_read_committed_profiles():
                          capture_output=True, text=True, check=True).stdout
     assert "b200::xattn_fused_kernel<160>" in out and "b200::gemm2_tc_kernel" in out
     assert "this library's kernels" in out.splitlines()[0]
+
+
+def test_product_path_never_touches_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use oracle/: no module
+    of the package imports it, and bench.py imports it only inside the CPU arm (class CpuArm)"""
+    import ast
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            hits += [(node.lineno, n) for n in names if n == "oracle" or n.startswith("oracle.")]
+        return tree, hits
+
+    pkg = os.path.join(root, "llm-groundeddiffusion_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert oracle_imports(os.path.join(d, f))[1] == [], os.path.join(d, f)
+    tree, hits = oracle_imports(os.path.join(root, "bench.py"))
+    arm = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CpuArm"][0]
+    lo, hi = arm.lineno, max(getattr(n, "end_lineno", arm.lineno) for n in ast.walk(arm) if hasattr(n, "end_lineno"))
+    assert hits and all(lo <= line <= hi for line, _ in hits), (hits, lo, hi)
